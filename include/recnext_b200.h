@@ -1,0 +1,101 @@
+/*
+ * recnext_b200.h — C ABI of the B200-native RecConv hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native layer: its hot path is the
+ * Python module RecConv2d (reference model/recnext.py:8-34), whose arithmetic is dispatched to ATen.  These
+ * entry points are what a binding for that module calls instead of ATen:
+ *
+ *   recconv_forward   replaces  RecConv2d.forward          model/recnext.py:24-34
+ *                               (down loop :27-29, up loop :31-33, final conv :34)
+ *   recconv_backward  replaces  the autograd graph of the same lines (conv dgrad/wgrad, upsample backward)
+ *   recconv_*_workspace_bytes / recconv_plan_describe: sizing and introspection helpers
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers owned by the caller (PyTorch); the library borrows them for
+ *     the duration of the stream-ordered call.  It never allocates or frees device memory, never
+ *     synchronises the device, and launches only on `stream` (safe under CUDA-graph capture).
+ *   - Layout is NCHW contiguous (what the reference feeds the module).  Every (n, c) plane is independent.
+ *   - Parameters follow the reference state_dict (model/recnext.py:21-22): `down.weight` [C,1,k,k],
+ *     `convs.{j}.weight` [C,1,k,k] for j = 0..level, optional `down.bias` / `convs.{j}.bias` [C].
+ *     They are passed as HOST arrays of device pointers so that no packing kernel is needed.
+ *   - Return value: 0 on success, a negative RECNEXT_E* code otherwise; recnext_last_error() returns a
+ *     thread-local message.  There is no CPU fallback: unsupported arguments are errors.
+ */
+#ifndef RECNEXT_B200_H_
+#define RECNEXT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RECNEXT_ABI_VERSION 1
+
+/* element types of x / y / gy / gx (dtype) and of the parameters (wdtype) */
+#define RECNEXT_F32 0
+#define RECNEXT_BF16 1
+#define RECNEXT_F16 2
+
+/* interpolation modes of F.interpolate(..., size=s, mode=...) (model/recnext.py:33) */
+#define RECNEXT_BILINEAR 0
+#define RECNEXT_NEAREST 1
+
+#define RECNEXT_MAX_LEVEL 6
+
+#define RECNEXT_OK 0
+#define RECNEXT_EINVAL (-1)     /* bad argument (shape, dtype, k, level, mode, null pointer) */
+#define RECNEXT_EUNSUPPORTED (-2) /* valid for the reference but not built here (e.g. plane too large) */
+#define RECNEXT_EWORKSPACE (-3) /* workspace too small */
+#define RECNEXT_ECUDA (-4)      /* CUDA runtime error at launch */
+
+typedef struct recconv_desc {
+    int32_t B, C, H, W;   /* input  x: [B, C, H, W] */
+    int32_t k;            /* odd kernel size: 3, 5 or 7 (reference default 5) */
+    int32_t level;        /* number of stride-2 downsamples, 0..RECNEXT_MAX_LEVEL */
+    int32_t mode;         /* RECNEXT_BILINEAR | RECNEXT_NEAREST */
+    int32_t dtype;        /* RECNEXT_F32 | RECNEXT_BF16 | RECNEXT_F16 : x, y, gy, gx */
+    int32_t wdtype;       /* dtype of weights and biases (F32 master weights, or same as dtype) */
+    int32_t has_bias;     /* 0 | 1 */
+} recconv_desc;
+
+typedef struct recconv_params {
+    const void* w_down;                              /* [C,1,k,k]   down.weight          */
+    const void* w_convs[RECNEXT_MAX_LEVEL + 1];      /* [C,1,k,k]   convs.{j}.weight     */
+    const void* b_down;                              /* [C] or NULL down.bias            */
+    const void* b_convs[RECNEXT_MAX_LEVEL + 1];      /* [C] or NULL convs.{j}.bias       */
+} recconv_params;
+
+int recnext_abi_version(void);
+const char* recnext_last_error(void);
+
+/* y = RecConv2d(x).  No workspace needed. */
+int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream);
+
+/*
+ * Backward.  gx: [B,C,H,W] in d->dtype.  Weight grads are fp32 and PACKED:
+ *   gw [(level+2), C, k*k]: slot 0 = down.weight (summed over all levels — the filter is shared,
+ *                            model/recnext.py:21,28), slot 1+j = convs.{j}.weight
+ *   gb [(level+2), C] or NULL (same slot order); must be non-NULL iff has_bias.
+ * Both are overwritten (not accumulated).  The result is deterministic (fixed reduction order).
+ * workspace: recconv_backward_workspace_bytes(d) bytes of device memory, 16-byte aligned.
+ */
+size_t recconv_backward_workspace_bytes(const recconv_desc* d);
+int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx,
+                     float* gw, float* gb, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
+int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);
+
+/*
+ * Source-index tables the kernels use for F.interpolate(size=out) from `in` (bit-exact contract with ATen
+ * UpSample.h:259-311,441-476).  Host-side helper for tests/diagnostics: fills i0[out], i1[out], lambda[out]
+ * (bilinear) or i0[out] only (nearest; i1/lambda may be NULL).
+ */
+int recconv_source_index(int mode, int in_size, int out_size, int32_t* i0, int32_t* i1, float* lambda);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECNEXT_B200_H_ */

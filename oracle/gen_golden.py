@@ -69,7 +69,8 @@ def recconv_case(name, B, C, H, W, L, k, mode, bias, seed=0):
 def index_tables():
     """F.interpolate on index ramps: the values ARE the source coordinates (bit-exact check)."""
     pairs = [(4, 7), (7, 14), (14, 28), (28, 56), (13, 25), (21, 42), (25, 50), (42, 84), (84, 167), (84, 168),
-             (3, 5), (2, 3), (1, 2), (1, 3), (1, 1), (5, 9), (6, 11), (12, 23), (15, 29), (8, 15), (100, 200)]
+             (3, 5), (2, 3), (1, 2), (1, 3), (1, 1), (5, 9), (6, 11), (12, 23), (15, 29), (8, 15), (100, 200),
+             (129, 257)]  # 129->257: the one pair below 400 where fused vs unfused src differ (dst 128)
     d = {}
     for i, o in pairs:
         ramp = torch.arange(i, dtype=torch.float32).view(1, 1, 1, i)

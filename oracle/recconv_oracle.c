@@ -57,7 +57,9 @@ static void round_buf(float* p, long n, int on) {
 void recconv_oracle_bilinear_index(int in_size, int out_size, int dst, int* i0, int* i1, float* lambda1) {
     if (out_size == in_size) { *i0 = dst; *i1 = dst; *lambda1 = 0.0f; return; }
     const float scale = (float)in_size / (float)out_size;
-    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    /* torch 2.11's ATen evaluates scale*(dst+0.5)-0.5 as ONE fused multiply-add, on CPU (probe:
+     * 129->257, dst 128 gives i0=63, lambda=0.999996) and on CUDA (nvcc contracts it), so fmaf it is. */
+    float src = fmaf(scale, (float)dst + 0.5f, -0.5f);
     if (src < 0.0f) src = 0.0f;
     int idx = (int)floorf(src);
     if (idx > in_size - 1) idx = in_size - 1;

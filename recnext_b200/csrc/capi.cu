@@ -1,0 +1,216 @@
+// capi.cu — extern "C" entry points of librecnext_b200.so (see include/recnext_b200.h).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/recnext_b200.h"
+#include "recconv_body.cuh"
+
+namespace recnext {
+typedef cudaError_t (*rc_launch_fn)(const Plan&, const KernelArgs&, cudaStream_t);
+template <int K, typename T, bool BWD> cudaError_t rc_launch(const Plan&, const KernelArgs&, cudaStream_t);
+
+#define RC_DECLARE_K(K)                                                                                       \
+    extern template cudaError_t rc_launch<K, float, false>(const Plan&, const KernelArgs&, cudaStream_t);     \
+    extern template cudaError_t rc_launch<K, float, true>(const Plan&, const KernelArgs&, cudaStream_t);      \
+    extern template cudaError_t rc_launch<K, __nv_bfloat16, false>(const Plan&, const KernelArgs&, cudaStream_t); \
+    extern template cudaError_t rc_launch<K, __nv_bfloat16, true>(const Plan&, const KernelArgs&, cudaStream_t);  \
+    extern template cudaError_t rc_launch<K, __half, false>(const Plan&, const KernelArgs&, cudaStream_t);    \
+    extern template cudaError_t rc_launch<K, __half, true>(const Plan&, const KernelArgs&, cudaStream_t);
+RC_DECLARE_K(3)
+RC_DECLARE_K(5)
+RC_DECLARE_K(7)
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+template <int K>
+static rc_launch_fn pick_dtype(int dtype, bool bwd) {
+    switch (dtype) {
+        case RECNEXT_F32: return bwd ? rc_launch<K, float, true> : rc_launch<K, float, false>;
+        case RECNEXT_BF16: return bwd ? rc_launch<K, __nv_bfloat16, true> : rc_launch<K, __nv_bfloat16, false>;
+        case RECNEXT_F16: return bwd ? rc_launch<K, __half, true> : rc_launch<K, __half, false>;
+    }
+    return nullptr;
+}
+static rc_launch_fn pick(int k, int dtype, bool bwd) {
+    switch (k) {
+        case 3: return pick_dtype<3>(dtype, bwd);
+        case 5: return pick_dtype<5>(dtype, bwd);
+        case 7: return pick_dtype<7>(dtype, bwd);
+    }
+    return nullptr;
+}
+
+static int device_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            sms = v;
+        else
+            return 148;  // B200; used only for planning when no device is visible (plan_describe on a CPU box)
+    }
+    return sms;
+}
+
+static int check_desc(const recconv_desc* d) {
+    if (!d) return fail(RECNEXT_EINVAL, "recconv: null descriptor");
+    if (d->B < 0 || d->C < 0 || d->H < 1 || d->W < 1) return fail(RECNEXT_EINVAL, "recconv: bad shape [%d,%d,%d,%d]", d->B, d->C, d->H, d->W);
+    if (!(d->k == 3 || d->k == 5 || d->k == 7)) return fail(RECNEXT_EINVAL, "recconv: kernel_size %d not in {3,5,7}", d->k);
+    if (d->level < 0 || d->level > RECNEXT_MAX_LEVEL) return fail(RECNEXT_EINVAL, "recconv: level %d outside 0..%d", d->level, RECNEXT_MAX_LEVEL);
+    if (d->mode != RECNEXT_BILINEAR && d->mode != RECNEXT_NEAREST) return fail(RECNEXT_EINVAL, "recconv: mode %d (0 bilinear, 1 nearest)", d->mode);
+    if (d->dtype < 0 || d->dtype > 2) return fail(RECNEXT_EINVAL, "recconv: dtype %d", d->dtype);
+    if (d->wdtype != RECNEXT_F32 && d->wdtype != d->dtype) return fail(RECNEXT_EINVAL, "recconv: parameters must be fp32 or match dtype");
+    return 0;
+}
+
+static int make_plan(const recconv_desc* d, bool bwd, Plan& pl) {
+    PlanOptions opt;
+    opt.num_sms = device_sms();
+    const int rc = rc_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, bwd ? 1 : 0, opt);
+    if (rc == 1)
+        return fail(RECNEXT_EUNSUPPORTED, "recconv: a %dx%d plane pyramid (level %d, %s) does not fit in 227 KB of shared memory",
+                    d->H, d->W, d->level, bwd ? "backward" : "forward");
+    if (rc) return fail(RECNEXT_EINVAL, "recconv: bad arguments");
+    return 0;
+}
+
+static int fill_args(const recconv_desc* d, const recconv_params* p, KernelArgs& a) {
+    if (!p) return fail(RECNEXT_EINVAL, "recconv: null params");
+    memset(&a, 0, sizeof(a));
+    a.w[0] = p->w_down; a.b[0] = d->has_bias ? p->b_down : nullptr;
+    if (d->level > 0 && !p->w_down) return fail(RECNEXT_EINVAL, "recconv: down.weight is null");
+    if (d->level > 0 && d->has_bias && !p->b_down) return fail(RECNEXT_EINVAL, "recconv: down.bias is null");
+    for (int j = 0; j <= d->level; ++j) {
+        if (!p->w_convs[j]) return fail(RECNEXT_EINVAL, "recconv: convs.%d.weight is null", j);
+        if (d->has_bias && !p->b_convs[j]) return fail(RECNEXT_EINVAL, "recconv: convs.%d.bias is null", j);
+        a.w[1 + j] = p->w_convs[j];
+        a.b[1 + j] = d->has_bias ? p->b_convs[j] : nullptr;
+    }
+    return 0;
+}
+
+__global__ void recconv_wgrad_finalize(const float* __restrict__ partial, float* __restrict__ gw, float* __restrict__ gb,
+                                       int n_chunk, int nstage, int C, int KK) {
+    const int ws = KK + 1;
+    const long total = (long)nstage * C * ws;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long sc = i / ws;
+        const int e = (int)(i - sc * ws);
+        float s = 0.f;
+        for (int ch = 0; ch < n_chunk; ++ch) s += partial[(long)ch * total + i];
+        if (e < KK) gw[sc * KK + e] = s;
+        else if (gb) gb[sc] = s;
+    }
+}
+
+}  // namespace recnext
+
+using namespace recnext;
+
+extern "C" {
+
+int recnext_abi_version(void) { return RECNEXT_ABI_VERSION; }
+const char* recnext_last_error(void) { return g_err; }
+
+int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream) {
+    if (int rc = check_desc(d)) return rc;
+    if (d->B == 0 || d->C == 0) return RECNEXT_OK;
+    if (!x || !y) return fail(RECNEXT_EINVAL, "recconv_forward: null tensor");
+    KernelArgs a;
+    if (int rc = fill_args(d, p, a)) return rc;
+    Plan pl;
+    if (int rc = make_plan(d, false, pl)) return rc;
+    a.x = x; a.out = y;
+    rc_launch_fn fn = pick(d->k, d->dtype, false);
+    const cudaError_t e = fn(pl, a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward: %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
+}
+
+size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
+    if (check_desc(d)) return 0;
+    if (d->B == 0 || d->C == 0) return 0;
+    Plan pl;
+    if (make_plan(d, true, pl)) return 0;
+    return (size_t)pl.ws_partial_floats * sizeof(float);
+}
+
+int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx, float* gw,
+                     float* gb, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_desc(d)) return rc;
+    if (!gw) return fail(RECNEXT_EINVAL, "recconv_backward: gw is null");
+    if ((d->has_bias != 0) != (gb != nullptr)) return fail(RECNEXT_EINVAL, "recconv_backward: gb must be given iff has_bias");
+    const int KK = d->k * d->k;
+    if (d->B == 0 || d->C == 0) {
+        if (d->C) {
+            cudaMemsetAsync(gw, 0, sizeof(float) * (d->level + 2) * d->C * KK, (cudaStream_t)stream);
+            if (gb) cudaMemsetAsync(gb, 0, sizeof(float) * (d->level + 2) * d->C, (cudaStream_t)stream);
+        }
+        return RECNEXT_OK;
+    }
+    if (!x || !gy || !gx) return fail(RECNEXT_EINVAL, "recconv_backward: null tensor");
+    KernelArgs a;
+    if (int rc = fill_args(d, p, a)) return rc;
+    Plan pl;
+    if (int rc = make_plan(d, true, pl)) return rc;
+    const size_t need = (size_t)pl.ws_partial_floats * sizeof(float);
+    if (!workspace || workspace_bytes < need)
+        return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
+    a.x = x; a.gy = gy; a.out = gx; a.partial = reinterpret_cast<float*>(workspace);
+    rc_launch_fn fn = pick(d->k, d->dtype, true);
+    cudaError_t e = fn(pl, a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward: %s", cudaGetErrorString(e));
+    const long total = (long)(d->level + 2) * d->C * (KK + 1);
+    const int threads = 256;
+    const int blocks = (int)((total + threads - 1) / threads);
+    recconv_wgrad_finalize<<<blocks, threads, 0, (cudaStream_t)stream>>>(a.partial, gw, gb, pl.n_chunk, d->level + 2, d->C, KK);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward(finalize): %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
+}
+
+int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen) {
+    if (int rc = check_desc(d)) return rc;
+    if (!buf || !buflen) return fail(RECNEXT_EINVAL, "recconv_plan_describe: null buffer");
+    Plan pl;
+    if (int rc = make_plan(d, backward != 0, pl)) return rc;
+    int n = snprintf(buf, buflen,
+                     "%s k=%d L=%d [%d,%d,%d,%d] planes/CTA=%d lanes/plane=%d threads=%d grid=%dx%d (cg x chunk, %d img/chunk) "
+                     "smem=%d B plane=%d B tma=%d rpi=",
+                     backward ? "bwd" : "fwd", pl.K, pl.L, pl.B, pl.C, pl.H, pl.W, pl.P, pl.g, pl.T, pl.n_cg, pl.n_chunk,
+                     pl.img_per_chunk, pl.smem_bytes, pl.plane_floats * 4, pl.use_tma);
+    for (int l = 0; l <= pl.L && n > 0 && (size_t)n < buflen; ++l)
+        n += snprintf(buf + n, buflen - n, "%s%d/%d", l ? "," : "", pl.lv[l].rpi, pl.lv[l].rpi_down);
+    return RECNEXT_OK;
+}
+
+int recconv_source_index(int mode, int in_size, int out_size, int32_t* i0, int32_t* i1, float* lambda) {
+    if (in_size < 1 || out_size < 1 || !i0) return fail(RECNEXT_EINVAL, "recconv_source_index: bad arguments");
+    for (int d = 0; d < out_size; ++d) {
+        if (mode == RECNEXT_NEAREST) {
+            i0[d] = rc_nearest_src(in_size, out_size, d);
+            if (i1) i1[d] = i0[d];
+            if (lambda) lambda[d] = 0.f;
+        } else {
+            int a, b; float l;
+            rc_bilinear_src(in_size, out_size, d, a, b, l);
+            i0[d] = a;
+            if (i1) i1[d] = b;
+            if (lambda) lambda[d] = l;
+        }
+    }
+    return RECNEXT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+// Fused RecConv kernels for kernel_size = 7 (all element types, forward and backward).
+#include "recconv_device.cuh"
+namespace recnext { RC_INSTANTIATE_K(7) }
