@@ -33,6 +33,12 @@ extern "C" {
 
 #define RECNEXT_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define RECNEXT_API __attribute__((visibility("default")))
+#else
+#define RECNEXT_API
+#endif
+
 /* element types of x / y / gy / gx (dtype) and of the parameters (wdtype) */
 #define RECNEXT_F32 0
 #define RECNEXT_BF16 1
@@ -67,11 +73,11 @@ typedef struct recconv_params {
     const void* b_convs[RECNEXT_MAX_LEVEL + 1];      /* [C] or NULL convs.{j}.bias       */
 } recconv_params;
 
-int recnext_abi_version(void);
-const char* recnext_last_error(void);
+RECNEXT_API int recnext_abi_version(void);
+RECNEXT_API const char* recnext_last_error(void);
 
 /* y = RecConv2d(x).  No workspace needed. */
-int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream);
+RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream);
 
 /*
  * Backward.  gx: [B,C,H,W] in d->dtype.  Weight grads are fp32 and PACKED:
@@ -81,19 +87,19 @@ int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* 
  * Both are overwritten (not accumulated).  The result is deterministic (fixed reduction order).
  * workspace: recconv_backward_workspace_bytes(d) bytes of device memory, 16-byte aligned.
  */
-size_t recconv_backward_workspace_bytes(const recconv_desc* d);
-int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx,
+RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d);
+RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx,
                      float* gw, float* gb, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
-int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);
+RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);
 
 /*
  * Source-index tables the kernels use for F.interpolate(size=out) from `in` (bit-exact contract with ATen
  * UpSample.h:259-311,441-476).  Host-side helper for tests/diagnostics: fills i0[out], i1[out], lambda[out]
  * (bilinear) or i0[out] only (nearest; i1/lambda may be NULL).
  */
-int recconv_source_index(int mode, int in_size, int out_size, int32_t* i0, int32_t* i1, float* lambda);
+RECNEXT_API int recconv_source_index(int mode, int in_size, int out_size, int32_t* i0, int32_t* i1, float* lambda);
 
 #ifdef __cplusplus
 }

@@ -120,10 +120,10 @@ using namespace recnext;
 
 extern "C" {
 
-int recnext_abi_version(void) { return RECNEXT_ABI_VERSION; }
-const char* recnext_last_error(void) { return g_err; }
+RECNEXT_API int recnext_abi_version(void) { return RECNEXT_ABI_VERSION; }
+RECNEXT_API const char* recnext_last_error(void) { return g_err; }
 
-int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream) {
+RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream) {
     if (int rc = check_desc(d)) return rc;
     if (d->B == 0 || d->C == 0) return RECNEXT_OK;
     if (!x || !y) return fail(RECNEXT_EINVAL, "recconv_forward: null tensor");
@@ -138,7 +138,7 @@ int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* 
     return RECNEXT_OK;
 }
 
-size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
+RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
     if (check_desc(d)) return 0;
     if (d->B == 0 || d->C == 0) return 0;
     Plan pl;
@@ -146,7 +146,7 @@ size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
     return (size_t)pl.ws_partial_floats * sizeof(float);
 }
 
-int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx, float* gw,
+RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx, float* gw,
                      float* gb, void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = check_desc(d)) return rc;
     if (!gw) return fail(RECNEXT_EINVAL, "recconv_backward: gw is null");
@@ -180,7 +180,7 @@ int recconv_backward(const recconv_desc* d, const recconv_params* p, const void*
     return RECNEXT_OK;
 }
 
-int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen) {
+RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen) {
     if (int rc = check_desc(d)) return rc;
     if (!buf || !buflen) return fail(RECNEXT_EINVAL, "recconv_plan_describe: null buffer");
     Plan pl;
@@ -195,7 +195,7 @@ int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t
     return RECNEXT_OK;
 }
 
-int recconv_source_index(int mode, int in_size, int out_size, int32_t* i0, int32_t* i1, float* lambda) {
+RECNEXT_API int recconv_source_index(int mode, int in_size, int out_size, int32_t* i0, int32_t* i1, float* lambda) {
     if (in_size < 1 || out_size < 1 || !i0) return fail(RECNEXT_EINVAL, "recconv_source_index: bad arguments");
     for (int d = 0; d < out_size; ++d) {
         if (mode == RECNEXT_NEAREST) {
