@@ -1,0 +1,229 @@
+"""RecNeXt M-series classifier — host-side mirror of the reference model definition around the RecConv hot path.
+
+The callers of the hot path: ``MetaNeXtBlock`` = ``x + drop_path(mlp(BN(RecConv2d(x))))``
+(reference model/recnext.py:149-158), stem / downsample / classifier (:134-201), the variants m0..m5 (:365-407)
+and BN folding for the fused-BN eval model (ConvNorm.fuse :75-97, NormLinear.fuse :109-122,
+RecNextClassifier.fuse :191-201, utils.replace_batchnorm utils.py:227-234).  Module names are kept so that the
+``state_dict`` keys and shapes are identical to the reference's (released checkpoints load with strict=True);
+everything except the token mixer is plain PyTorch (out of scope for the CUDA work).
+
+``token_mixer`` lets a caller pick the RecConv2d implementation; the default is the CUDA one.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+import torch.nn as nn
+
+from .recconv import RecConv2d
+
+VARIANTS = {  # reference model/recnext.py:369-406
+    "recnext_m0": dict(embed_dim=(40, 80, 160, 320), depth=(2, 2, 9, 1)),
+    "recnext_m1": dict(embed_dim=(48, 96, 192, 384), depth=(3, 3, 15, 2)),
+    "recnext_m2": dict(embed_dim=(56, 112, 224, 448), depth=(3, 3, 15, 2)),
+    "recnext_m3": dict(embed_dim=(64, 128, 256, 512), depth=(3, 3, 13, 2)),
+    "recnext_m4": dict(embed_dim=(64, 128, 256, 512), depth=(5, 5, 25, 4)),
+    "recnext_m5": dict(embed_dim=(80, 160, 320, 640), depth=(7, 7, 35, 2)),
+}
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (what timm.layers.DropPath does in training mode)."""
+
+    def __init__(self, p: float = 0.0):
+        super().__init__()
+        self.p = float(p)
+
+    def forward(self, x):
+        if self.p == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.p
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask.div_(keep)
+
+
+class ConvNorm(nn.Sequential):
+    """conv (no bias) + BatchNorm2d; ``fuse()`` folds the running statistics into a biased conv."""
+
+    def __init__(self, cin, cout, kernel_size=1, stride=1, padding=0, groups=1):
+        super().__init__()
+        self.add_module("conv", nn.Conv2d(cin, cout, kernel_size, stride, padding, groups=groups, bias=False))
+        self.add_module("norm", nn.BatchNorm2d(cout))
+
+    @torch.no_grad()
+    def fuse(self) -> nn.Conv2d:
+        conv, bn = self.conv, self.norm
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        shift = bn.bias - scale * bn.running_mean
+        if conv.bias is not None:
+            shift = shift + scale * conv.bias
+        out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
+                        conv.groups, bias=True, device=conv.weight.device, dtype=conv.weight.dtype)
+        out.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
+        out.bias.copy_(shift)
+        return out
+
+
+class NormLinear(nn.Sequential):
+    """BatchNorm1d + Linear; ``fuse()`` folds the norm into the linear layer."""
+
+    def __init__(self, cin, cout, std=0.02):
+        super().__init__()
+        self.add_module("norm", nn.BatchNorm1d(cin))
+        self.add_module("linear", nn.Linear(cin, cout, bias=True))
+        nn.init.trunc_normal_(self.linear.weight, std=std)
+        nn.init.zeros_(self.linear.bias)
+
+    @torch.no_grad()
+    def fuse(self) -> nn.Linear:
+        bn, lin = self.norm, self.linear
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        shift = bn.bias - bn.running_mean * scale
+        out = nn.Linear(lin.in_features, lin.out_features, device=lin.weight.device, dtype=lin.weight.dtype)
+        out.weight.copy_(lin.weight * scale.view(1, -1))
+        out.bias.copy_(lin.weight @ shift + lin.bias)
+        return out
+
+
+def mlp(cin: int, hidden: int, act_layer=nn.GELU) -> nn.Sequential:
+    hidden = int(hidden)
+    return nn.Sequential(ConvNorm(cin, hidden, 1), act_layer(), ConvNorm(hidden, cin, 1))
+
+
+class RecNextStem(nn.Module):
+    def __init__(self, cin, cout, act_layer=nn.GELU):
+        super().__init__()
+        self.stem = nn.Sequential(ConvNorm(cin, cout // 2, 3, 2, 1), act_layer(), ConvNorm(cout // 2, cout, 3, 2, 1))
+
+    def forward(self, x):
+        return self.stem(x)
+
+
+class MetaNeXtBlock(nn.Module):
+    """x + drop_path(channel_mixer(norm(token_mixer(x)))), token_mixer = RecConv2d(level = 4 - stage, k = 5)."""
+
+    def __init__(self, dim, mlp_ratio, act_layer=nn.GELU, stage=0, drop_path=0.0, token_mixer: Callable = RecConv2d):
+        super().__init__()
+        self.token_mixer = token_mixer(dim, level=4 - stage, kernel_size=5)
+        self.norm = nn.BatchNorm2d(dim)
+        self.channel_mixer = mlp(dim, dim * mlp_ratio, act_layer)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+
+    def forward(self, x):
+        return x + self.drop_path(self.channel_mixer(self.norm(self.token_mixer(x))))
+
+
+class Downsample(nn.Module):
+    def __init__(self, dim, mlp_ratio, act_layer=nn.GELU):
+        super().__init__()
+        self.token_mixer = nn.Conv2d(dim, dim * 2, kernel_size=7, padding=3, groups=dim, stride=2)
+        self.norm = nn.BatchNorm2d(dim * 2)
+        self.channel_mixer = mlp(dim * 2, dim * 2 * mlp_ratio, act_layer)
+
+    def forward(self, x):
+        x = self.norm(self.token_mixer(x))
+        return x + self.channel_mixer(x)
+
+
+class RecNextClassifier(nn.Module):
+    def __init__(self, dim, num_classes, distillation=False):
+        super().__init__()
+        self.num_classes, self.distillation = num_classes, distillation
+        self.head_drop = nn.Dropout(0.0)
+        self.head = NormLinear(dim, num_classes) if num_classes > 0 else nn.Identity()
+        self.head_dist = NormLinear(dim, num_classes) if num_classes > 0 else nn.Identity()
+
+    def forward(self, x):
+        x = self.head_drop(x)
+        a, b = self.head(x), self.head_dist(x)
+        if self.training and self.distillation:
+            return a, b
+        return (a + b) / 2
+
+    @torch.no_grad()
+    def fuse(self):
+        if not self.num_classes > 0:
+            return nn.Identity()
+        a, b = self.head.fuse(), self.head_dist.fuse()
+        a.weight.copy_((a.weight + b.weight) / 2)
+        a.bias.copy_((a.bias + b.bias) / 2)
+        return a
+
+
+class RecNextStage(nn.Module):
+    def __init__(self, cin, cout, depth, mlp_ratio, act_layer, downsample, stage, drop_path, token_mixer):
+        super().__init__()
+        self.downsample = Downsample(cin, mlp_ratio, act_layer) if downsample else nn.Identity()
+        self.blocks = nn.Sequential(*[MetaNeXtBlock(cout, mlp_ratio, act_layer, stage, drop_path, token_mixer) for _ in range(depth)])
+
+    def forward(self, x):
+        return self.blocks(self.downsample(x))
+
+
+class RecNext(nn.Module):
+    def __init__(self, in_chans=3, embed_dim: Sequence[int] = (48,), depth: Sequence[int] = (2,), mlp_ratio=2, num_classes=1000,
+                 act_layer=nn.GELU, distillation=False, drop_rate=0.0, drop_path=0.0, token_mixer: Callable = RecConv2d):
+        super().__init__()
+        self.embed_dim, self.num_classes, self.num_features = tuple(embed_dim), num_classes, embed_dim[-1]
+        self.stem = RecNextStem(in_chans, embed_dim[0], act_layer)
+        stages, cin = [], embed_dim[0]
+        for i, (dim, d) in enumerate(zip(embed_dim, depth)):
+            stages.append(RecNextStage(cin, dim, d, mlp_ratio, act_layer, i != 0, i, drop_path, token_mixer))
+            cin = dim
+        self.stages = nn.Sequential(*stages)
+        self.head_drop = nn.Dropout(drop_rate)
+        self.head = RecNextClassifier(embed_dim[-1], num_classes, distillation)
+
+    def forward_features(self, x):
+        return self.stages(self.stem(x))
+
+    def forward_head(self, x):
+        return self.head(self.head_drop(x.mean((2, 3))))
+
+    def forward(self, x):
+        return self.forward_head(self.forward_features(x))
+
+    @torch.no_grad()
+    def fuse(self):
+        replace_batchnorm(self)
+
+
+def replace_batchnorm(net: nn.Module) -> nn.Module:
+    """Recursively swaps every child that has ``fuse()`` for its fused form (reference utils.py:227-234).
+    As in the reference, MetaNeXtBlock.norm / Downsample.norm have no ``fuse`` and stay as BatchNorm2d."""
+    for name, child in list(net.named_children()):
+        if hasattr(child, "fuse"):
+            fused = child.fuse()
+            setattr(net, name, fused)
+            replace_batchnorm(fused)
+        else:
+            replace_batchnorm(child)
+    return net
+
+
+def create_model(variant: str, token_mixer: Callable = RecConv2d, **kwargs) -> RecNext:
+    """``create_model('recnext_m3')`` — the timm entry point the reference registers (model/recnext.py:365-407)."""
+    if variant not in VARIANTS:
+        raise ValueError(f"unknown variant {variant!r}; available: {sorted(VARIANTS)}")
+    args = dict(VARIANTS[variant])
+    if variant in ("recnext_m4", "recnext_m5") and not kwargs.get("distillation", False):
+        args["drop_path"] = 0.2 if variant == "recnext_m4" else 0.3
+    args.update(kwargs)
+    return RecNext(token_mixer=token_mixer, **args)
+
+
+def swap_recconv(net: nn.Module, token_mixer: Callable = RecConv2d) -> nn.Module:
+    """Replaces every module that looks like the reference RecConv2d (has ``down``, ``convs``, ``level``, ``mode``) by
+    ``token_mixer`` carrying the same parameters — for models built from the reference's own code."""
+    for name, child in list(net.named_children()):
+        if all(hasattr(child, a) for a in ("down", "convs", "level", "mode")) and not isinstance(child, token_mixer):
+            k = child.down.kernel_size[0]
+            new = token_mixer(child.down.in_channels, kernel_size=k, bias=child.down.bias is not None, level=child.level,
+                              mode=child.mode)
+            new.load_state_dict(child.state_dict(), strict=True)
+            new.to(child.down.weight.device, child.down.weight.dtype)
+            setattr(net, name, new)
+        else:
+            swap_recconv(child, token_mixer)
+    return net

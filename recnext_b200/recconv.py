@@ -60,6 +60,24 @@ def _prep_params(x, weights, biases):
     return wd, ws, bs
 
 
+# ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream -------------
+_timing = None
+
+
+def timing_begin() -> None:
+    """Start bracketing every forward launch with CUDA events recorded on the launching stream."""
+    global _timing
+    _timing = []
+
+
+def timing_end():
+    """Stop; returns [{'bytes': algorithmic bytes (2*N*e), 'ms': device time, 'shape': ...}] per launch."""
+    global _timing
+    rec, _timing = _timing or [], None
+    torch.cuda.synchronize()
+    return [dict(bytes=b, ms=a.elapsed_time(z), shape=shape) for (a, z, b, shape) in rec]
+
+
 def recconv_forward(x: torch.Tensor, weights: List[torch.Tensor], biases: Optional[List[torch.Tensor]], k: int, level: int,
                     mode: str) -> torch.Tensor:
     """Functional forward.  weights = [down.weight, convs[0].weight, ..., convs[level].weight]."""
@@ -70,8 +88,14 @@ def recconv_forward(x: torch.Tensor, weights: List[torch.Tensor], biases: Option
     d = _desc(x, k, level, mode, wd, bs is not None)
     y = torch.empty_like(x)
     with torch.cuda.device(x.device):
+        if _timing is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         N.check(N.lib().recconv_forward(ctypes.byref(d), ctypes.byref(_params(ws, bs)), x.data_ptr(), y.data_ptr(), _stream(x)),
                 "recconv_forward")
+        if _timing is not None:
+            ev1.record()
+            _timing.append((ev0, ev1, 2 * x.numel() * x.element_size(), tuple(x.shape)))
     return y
 
 

@@ -1,0 +1,95 @@
+"""Host-side RecNeXt-M mirror: state_dict layout and logits against the reference fixtures (tests/golden/model_logits.npz,
+generated from the unmodified reference with oracle/detinit.py weights)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.detinit import fill_state_dict_
+from oracle.torch_ref import RefRecConv2d
+from tests.helpers import GOLDEN, rel_err
+
+Z = np.load(os.path.join(GOLDEN, "model_logits.npz"))
+
+
+def _inputs(res):
+    g = torch.Generator().manual_seed(1234)
+    return torch.randn(2, 3, res, res, generator=g)
+
+
+@pytest.mark.parametrize("variant", ["recnext_m0", "recnext_m3"])
+def test_state_dict_keys_match_reference(variant):
+    from recnext_b200.model import create_model
+
+    net = create_model(variant)
+    assert sorted(net.state_dict().keys()) == [str(k) for k in Z[f"{variant}_keys"]]
+    assert sum(p.numel() for p in net.parameters()) == int(Z[f"{variant}_224_nparams"])
+
+
+def test_host_model_logits_cpu_with_torch_token_mixer():
+    """The surrounding model code (stem, BN, mlp, downsample, head) reproduces the reference logits on CPU."""
+    from recnext_b200.model import create_model, replace_batchnorm
+
+    net = create_model("recnext_m0", token_mixer=RefRecConv2d).eval()
+    fill_state_dict_(net, seed=0)
+    with torch.no_grad():
+        y = net(_inputs(224)).numpy()
+        assert rel_err(y, Z["recnext_m0_224_logits"]) < 1e-4
+        replace_batchnorm(net)  # fused-BN eval model: same function
+        assert rel_err(net(_inputs(224)).numpy(), Z["recnext_m0_224_logits"]) < 1e-4
+    # after fusing, the un-fusable BatchNorm2d layers are exactly the block/downsample norms
+    n_bn = sum(isinstance(m, torch.nn.BatchNorm2d) for m in net.modules())
+    assert n_bn == sum((2, 2, 9, 1)) + 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,res", [("recnext_m0", 224), ("recnext_m3", 224), ("recnext_m0", 160)])
+def test_full_model_logits_gpu(variant, res):
+    """Full RecNeXt forward with the CUDA RecConv2d vs the reference's logits on identical inputs and weights."""
+    from recnext_b200.model import create_model, replace_batchnorm
+
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        net = create_model(variant).eval()
+        fill_state_dict_(net, seed=0)
+        net.cuda()
+        with torch.no_grad():
+            y = net(_inputs(res).cuda()).cpu().numpy()
+            assert rel_err(y, Z[f"{variant}_{res}_logits"]) < 1e-4
+            feats = net.forward_features(_inputs(res).cuda()).mean((2, 3)).cpu().numpy()
+            assert rel_err(feats, Z[f"{variant}_{res}_feat_mean"]) < 1e-4
+            replace_batchnorm(net)
+            assert rel_err(net(_inputs(res).cuda()).cpu().numpy(), Z[f"{variant}_{res}_logits"]) < 1e-4
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                yb = net(_inputs(res).cuda()).float().cpu().numpy()
+            assert rel_err(yb, Z[f"{variant}_{res}_logits"]) < 5e-2
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.gpu
+def test_model_training_step_gradients_gpu():
+    """One fwd+bwd of RecNeXt-M0 (training mode BN) with the CUDA token mixer vs the PyTorch restatement."""
+    from recnext_b200.model import create_model
+
+    torch.manual_seed(0)
+    a = create_model("recnext_m0").cuda().train()
+    b = create_model("recnext_m0", token_mixer=RefRecConv2d).cuda().train()
+    b.load_state_dict(a.state_dict(), strict=True)
+    x = torch.randn(4, 3, 128, 128, device="cuda")
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        la = a(x).logsumexp(1).mean(); la.backward()
+        lb = b(x).logsumexp(1).mean(); lb.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    assert abs(la.item() - lb.item()) < 1e-4 * max(1.0, abs(lb.item()))
+    worst = 0.0
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        worst = max(worst, rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()))
+    assert worst < 2e-3, worst
