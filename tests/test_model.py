@@ -89,7 +89,13 @@ def test_model_training_step_gradients_gpu():
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
     assert abs(la.item() - lb.item()) < 1e-4 * max(1.0, abs(lb.item()))
-    worst = 0.0
+    # biases in front of a training-mode BatchNorm have a mathematically zero gradient (pure rounding noise), so the
+    # error of every tensor is measured against max(|its reference gradient|, 1e-3 * largest gradient in the model)
+    gmax = max(float(q.grad.abs().max()) for q in b.parameters())
+    worst, worst_name = 0.0, None
     for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
-        worst = max(worst, rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()))
-    assert worst < 2e-3, worst
+        diff = float((p.grad - q.grad).abs().max())
+        e = diff / max(float(q.grad.abs().max()), 1e-3 * gmax)
+        if e > worst:
+            worst, worst_name = e, n
+    assert worst < 2e-3, (worst, worst_name)
