@@ -101,8 +101,7 @@ static int fill_args(const recconv_desc* d, const recconv_params* p, KernelArgs&
 }
 
 __global__ void recconv_wgrad_finalize(const float* __restrict__ partial, float* __restrict__ gw, float* __restrict__ gb,
-                                       int n_chunk, int nstage, int C, int KK) {
-    const int ws = KK + 1;
+                                       int n_chunk, int nstage, int C, int KK, int ws) {
     const long total = (long)nstage * C * ws;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long sc = i / ws;
@@ -110,7 +109,7 @@ __global__ void recconv_wgrad_finalize(const float* __restrict__ partial, float*
         float s = 0.f;
         for (int ch = 0; ch < n_chunk; ++ch) s += partial[(long)ch * total + i];
         if (e < KK) gw[sc * KK + e] = s;
-        else if (gb) gb[sc] = s;
+        else if (e == KK && gb) gb[sc] = s;
     }
 }
 
@@ -171,10 +170,10 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
     rc_launch_fn fn = pick(d->k, d->dtype, true);
     cudaError_t e = fn(pl, a, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward: %s", cudaGetErrorString(e));
-    const long total = (long)(d->level + 2) * d->C * (KK + 1);
+    const long total = (long)(d->level + 2) * d->C * pl.wstride;
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads);
-    recconv_wgrad_finalize<<<blocks, threads, 0, (cudaStream_t)stream>>>(a.partial, gw, gb, pl.n_chunk, d->level + 2, d->C, KK);
+    recconv_wgrad_finalize<<<blocks, threads, 0, (cudaStream_t)stream>>>(a.partial, gw, gb, pl.n_chunk, d->level + 2, d->C, KK, pl.wstride);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward(finalize): %s", cudaGetErrorString(e));
     return RECNEXT_OK;
@@ -186,10 +185,10 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
     Plan pl;
     if (int rc = make_plan(d, backward != 0, pl)) return rc;
     int n = snprintf(buf, buflen,
-                     "%s k=%d L=%d [%d,%d,%d,%d] planes/CTA=%d lanes/plane=%d threads=%d grid=%dx%d (cg x chunk, %d img/chunk) "
-                     "smem=%d B plane=%d B tma=%d rpi=",
-                     backward ? "bwd" : "fwd", pl.K, pl.L, pl.B, pl.C, pl.H, pl.W, pl.P, pl.g, pl.T, pl.n_cg, pl.n_chunk,
-                     pl.img_per_chunk, pl.smem_bytes, pl.plane_floats * 4, pl.use_tma);
+                     "%s k=%d L=%d [%d,%d,%d,%d] planes/CTA=%d lanes/plane=%d units=%d threads=%d grid=%dx%d (cg x chunk, %d img/chunk) "
+                     "smem=%d B plane=%d B tma=%d share_raw=%d rpi=",
+                     backward ? "bwd" : "fwd", pl.K, pl.L, pl.B, pl.C, pl.H, pl.W, pl.P, pl.g, pl.n_units, pl.T, pl.n_cg, pl.n_chunk,
+                     pl.img_per_chunk, pl.smem_bytes, pl.plane_floats * 4, pl.use_tma, pl.share_raw);
     for (int l = 0; l <= pl.L && n > 0 && (size_t)n < buflen; ++l)
         n += snprintf(buf + n, buflen - n, "%s%d/%d", l ? "," : "", pl.lv[l].rpi, pl.lv[l].rpi_down);
     return RECNEXT_OK;

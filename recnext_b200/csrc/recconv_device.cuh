@@ -62,23 +62,55 @@ __device__ __forceinline__ void rc_coop_copy(void* dst, const void* src, long by
     }
 }
 
+// transposed butterfly: after the call lane `r` of every GG-lane group holds, in v[j], the group total of element
+// base(r) + j, base(r) = r * (32 / GG) (elements padded to 32).  31 shuffles for GG = 32 instead of 5 per element.
+template <int GG, int N>
+__device__ __forceinline__ void rc_group_reduce(float (&v)[32], const float (&acc)[N], int r) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = i < N ? acc[i] : 0.f;
+    int cnt = 32;
+#pragma unroll
+    for (int s = GG / 2; s > 0; s >>= 1) {
+        const int half = cnt / 2;
+        const bool upper = (r & s) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < half) {
+                const float lo = v[i], hi = v[i + half];
+                const float send = upper ? lo : hi;
+                const float keep = upper ? hi : lo;
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+        }
+        cnt = half;
+    }
+}
+
 struct DeviceCtx {
-    int tid, T, use_tma;
+    int tid, T, use_tma, g, u, ul, unit_lanes;
     uint32_t bar, phase;
 
     template <class F> __device__ __forceinline__ void run(F f) { f(tid); }
-    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void cta_sync() { __syncthreads(); }
+    // teams / units never interact: a warp-resident unit needs only __syncwarp, a multi-warp team a named barrier
+    __device__ __forceinline__ void sync() {
+        if (unit_lanes <= 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(u + 1), "r"(unit_lanes) : "memory");
+    }
 
-    __device__ __forceinline__ void load_begin(void* d0, const void* s0, long b0, void* d1, const void* s1, long b1) {
+    template <class F> __device__ __forceinline__ void load_begin(F desc) {
+        void *d0, *d1; const void *s0, *s1; long b0, b1;
+        desc(u, d0, s0, b0, d1, s1, b1);
+        if (b0 + b1 == 0) return;
         if (use_tma) {
-            if (tid == 0) {
+            if (ul == 0) {
                 rc_mbar_expect_tx(bar, (uint32_t)(b0 + b1));
                 rc_bulk_g2s(d0, s0, (uint32_t)b0, bar);
                 if (b1) rc_bulk_g2s(d1, s1, (uint32_t)b1, bar);
             }
         } else {
-            rc_coop_copy(d0, s0, b0, tid, T);
-            if (b1) rc_coop_copy(d1, s1, b1, tid, T);
+            rc_coop_copy(d0, s0, b0, ul, unit_lanes);
+            if (b1) rc_coop_copy(d1, s1, b1, ul, unit_lanes);
         }
     }
     __device__ __forceinline__ void load_wait() {
@@ -86,48 +118,73 @@ struct DeviceCtx {
             while (!rc_mbar_try_wait(bar, phase)) {}
             phase ^= 1u;
         } else {
-            __syncthreads();
+            sync();
         }
     }
-    __device__ __forceinline__ void store(void* dst, const void* src, long bytes) {
+    template <class F> __device__ __forceinline__ void store(F desc) {
+        void* dst; const void* src; long bytes;
+        desc(u, dst, src, bytes);
         if (use_tma) {
             rc_fence_proxy_async();  // make this thread's shared-memory writes visible to the async proxy
-            __syncthreads();
-            if (tid == 0) rc_bulk_s2g(dst, src, (uint32_t)bytes);
+            sync();
+            if (ul == 0 && bytes) rc_bulk_s2g(dst, src, (uint32_t)bytes);
         } else {
-            __syncthreads();
-            rc_coop_copy(dst, src, bytes, tid, T);
+            sync();
+            rc_coop_copy(dst, src, bytes, ul, unit_lanes);
         }
     }
     __device__ __forceinline__ void store_drain() {
-        if (use_tma) { if (tid == 0) rc_bulk_wait_read0(); }
-        else __syncthreads();  // cooperative stores of the previous image have finished reading raw out
+        if (use_tma) { if (ul == 0) rc_bulk_wait_read0(); }
+        else sync();  // cooperative stores of the previous image have finished reading raw out
     }
 
-    // Sum the per-lane partials of one plane (g lanes, inside a warp) with xor-shuffles, then every lane adds
-    // "its" elements into the plane's (or warp's) accumulation slot: no atomics, fixed order.
+    // Sum the per-lane partials of one plane (team lanes inside a warp) with a transposed butterfly, then every
+    // lane adds "its" elements into the plane's (or warp's) accumulation slot: no atomics, fixed order.
     template <int N>
     __device__ __forceinline__ void wgrad_commit(const ThreadPos& t, const Plan& pl, float (&acc)[N], float* slot) {
-        const int gg = pl.g < 32 ? pl.g : 32;
-        for (int off = gg >> 1; off > 0; off >>= 1) {
+        static_assert(N <= 32 || N == 50, "kernel sizes 3, 5, 7");
+        if constexpr (N <= 32) {
+            float v[32];
+            const int gg = g < 32 ? g : 32;
+            const int r = tid & (gg - 1);
+            switch (gg) {
+                case 32: rc_group_reduce<32, N>(v, acc, r); break;
+                case 16: rc_group_reduce<16, N>(v, acc, r); break;
+                case 8: rc_group_reduce<8, N>(v, acc, r); break;
+                case 4: rc_group_reduce<4, N>(v, acc, r); break;
+                case 2: rc_group_reduce<2, N>(v, acc, r); break;
+                default: rc_group_reduce<1, N>(v, acc, r); break;
+            }
+            if (t.p < pl.P) {
+                const int per = 32 / gg, base = r * per;
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-        }
-        if (t.p < pl.P) {
-            const int r = t.tid & (gg - 1);
+                for (int j = 0; j < 32; ++j)
+                    if (j < per && base + j < N) slot[base + j] += v[j];
+            }
+        } else {  // k = 7: 50 values, plain xor butterfly per element
+            const int gg = g < 32 ? g : 32;
+            for (int off = gg >> 1; off > 0; off >>= 1) {
 #pragma unroll
-            for (int i = 0; i < N; ++i)
-                if ((i & (gg - 1)) == r) slot[i] += acc[i];
+                for (int i = 0; i < N; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+            }
+            if (t.p < pl.P) {
+                const int r = tid & (gg - 1);
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    if ((i & (gg - 1)) == r) slot[i] += acc[i];
+            }
         }
     }
 };
 
 template <int K, typename T, bool BWD>
-__global__ void __launch_bounds__(256) recconv_kernel(const __grid_constant__ Plan pl, const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(kMaxThreads, BWD ? 1 : 2) recconv_kernel(const __grid_constant__ Plan pl, const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     DeviceCtx ctx;
-    ctx.tid = threadIdx.x; ctx.T = pl.T; ctx.use_tma = pl.use_tma; ctx.bar = rc_smem_u32(smem); ctx.phase = 0;
-    if (pl.use_tma && threadIdx.x == 0) rc_mbar_init(ctx.bar, 1);
+    ctx.tid = threadIdx.x; ctx.T = pl.T; ctx.use_tma = pl.use_tma; ctx.g = pl.g; ctx.unit_lanes = pl.unit_lanes;
+    ctx.u = threadIdx.x / pl.unit_lanes; ctx.ul = threadIdx.x - ctx.u * pl.unit_lanes;
+    ctx.bar = rc_smem_u32(smem + pl.smBar + 8 * ctx.u); ctx.phase = 0;
+    if (pl.use_tma && ctx.ul == 0) rc_mbar_init(ctx.bar, 1);
     __syncthreads();
     const int cg = blockIdx.x % pl.n_cg, chunk = blockIdx.x / pl.n_cg;
     if (BWD) rc_backward_body<K, T>(ctx, pl, a, smem, cg, chunk);

@@ -1,12 +1,15 @@
 // recconv_plan.h — launch plan / shared-memory layout of the fused RecConv kernels.
 //
-// One CTA owns P consecutive (n, c) planes of ONE image ("plane group" = P consecutive channels, which are
-// contiguous in NCHW) and keeps the whole pyramid of those planes in shared memory; it walks over a chunk of
-// images for its channel group, so filters are loaded once and weight-gradient partials stay on chip.
-// Each plane is worked on by `g` lanes.  All geometry is decided on the host and passed by value.
+// Work decomposition.  Every (n, c) plane of RecConv2d is independent (all convs are depthwise, reference
+// model/recnext.py:13-22), so a plane is given to a TEAM of g lanes that keeps the plane's whole pyramid in
+// shared memory.  Teams never talk to each other: a team of g <= 32 lanes lives inside one warp and is
+// synchronised with __syncwarp(), a bigger team (g = 64..256) owns a named barrier.  A UNIT is what moves
+// through TMA together: one warp's teams (32/g consecutive planes) or one multi-warp team (one plane).
+// A CTA is P planes = n_units units of ONE image and walks over a chunk of images for its channel group, so
+// filters are loaded once and weight-gradient partials stay on chip.
 //
 // Padded level buffers: level l is stored as rows_l x pitch_l floats, interior at (row + pad, col + pad),
-// pad = k/2, everything outside the interior is zero for the whole kernel (zeroed once), which is what makes
+// pad = k/2; everything outside the interior is zero for the whole kernel (zeroed once), which is what makes
 // the stencil loops free of bounds checks (nn.Conv2d zero padding, reference model/recnext.py:18).
 #pragma once
 #include <stdint.h>
@@ -27,6 +30,7 @@ namespace recnext {
 
 constexpr int kMaxLevel = RECNEXT_MAX_LEVEL;
 constexpr int kStripW = 4;  // output columns per work item (one float4 of accumulators)
+constexpr int kMaxThreads = 256;
 
 struct LevelGeo {
     int H, W;        // level size (level 0 = input)
@@ -34,49 +38,76 @@ struct LevelGeo {
     int rows;        // padded rows
     int offS;        // float offset of S_l (x_l, then x_l + u_l) inside the plane block
     int offX;        // bwd: copy of x_l (levels 1..L-1), -1 if absent
-    int offGT;       // bwd: gradient w.r.t. t_l = convs[L-l](s_l) after upsample-backward (padded), levels 1..L
+    int offGT;       // bwd: gradient w.r.t. t_l = convs[L-l](s_l) (padded), levels 1..L
     int offGS;       // bwd: gradient w.r.t. s_l, later total gradient of x_l (padded), levels 1..L
     int rpi;         // rows per work item for stride-1 stencils ON this level
     int rpi_down;    // rows per work item for the stride-2 stencil PRODUCING this level (l >= 1)
-    int tabY, tabX;  // byte offsets (in the table region) of the forward interpolation tables that map
-                     // level l-1 coordinates to level l sources: {int i0; float lambda}[H_{l-1}] / [W_{l-1}]
-    int rngY, rngX;  // bwd: byte offsets of {int lo; int hi}[H_l] / [W_l]: destinations touching source i
+    int rpu;         // l >= 1: SOURCE rows per work item of the exact-2x upsample into level l-1
+    unsigned magic_W;  // magic for division by W (backward gather)
+    int nstrips;     // ceil(W / 4)
+    unsigned magic_strips;  // floor(2^32 / nstrips) + 1 : item / nstrips == umulhi(item, magic)
+    int tpitch;      // l >= 1: pitch of the T buffer of this level ((H+2) x tpitch, replicate border of 1)
+    int exact2x;     // l >= 1: level l-1 is exactly 2x this level in both dimensions (bilinear fast path)
+    int tabY, tabX;  // byte offsets (table region) of {int i0; float lambda}[H_{l-1}] / [W_{l-1}] (level l-1 -> l)
+    int gatY, gatX;  // bwd: byte offsets of GatherEntry[H_l] / [W_l]: destinations of level l-1 reading source i
 };
 
 struct Plan {
     int B, C, H, W, K, L, mode, dtype, wdtype, has_bias, backward;
     int P;             // planes (channels) per CTA
-    int g;             // lanes per plane (power of two <= 32, or a multiple of 32)
-    int T;             // threads per CTA = P * g
+    int g;             // lanes per plane (team size): power of two <= 256
+    int T;             // threads per CTA = P * g, a multiple of 32
+    int unit_lanes;    // lanes per unit = max(g, 32)
+    int ppu;           // planes per unit = 32 / g (g < 32) or 1
+    int n_units;       // units per CTA
     int n_cg;          // channel groups = ceil(C / P)
     int n_chunk;       // image chunks; grid = n_cg * n_chunk
     int img_per_chunk;
-    int use_tma;       // 1: cp.async.bulk loads/stores of whole plane groups (needs 16-byte alignment)
-    int share_raw;     // 1: the raw output buffer aliases a raw input buffer (big planes): no prefetch of the next image
+    int use_tma;       // 1: cp.async.bulk loads/stores of whole units (needs 16-byte alignment)
+    int share_raw;     // 1: raw output aliases a raw input buffer (big planes): no prefetch of the next image
     int esize;         // bytes per element of x
+    int vec;           // elements per unpack chunk: largest power of two dividing W, <= 16 / esize
+    unsigned magic_cpr;  // magic for division by chunks-per-row (W / vec)
     LevelGeo lv[kMaxLevel + 1];
-    int offT;          // float offset of T (unpadded conv output awaiting interpolation), fwd and bwd
+    int offT;          // float offset of T inside the plane block
     int offGY;         // bwd: padded gy (level-0 geometry)
     int offG0;         // bwd: gradient w.r.t. s_0 (unpadded, pitch = pitchG0)
     int pitchG0;
     int plane_floats;  // floats per plane block
     // byte offsets inside dynamic shared memory
-    int smTab, smW, smWG, smRawX, smRawG, smRawOut, smPlanes, smem_bytes;
-    int wstride;       // floats per (plane, conv) filter slot = K*K + 1 (bias last)
+    int smBar, smTab, smW, smWG, smRawX, smRawG, smRawOut, smPlanes, smem_bytes;
+    int raw_unit_bytes;  // bytes of one unit's raw buffer (padded to 128)
+    int wstride;       // floats per (plane, conv) filter slot = round_up(K*K + 1, 4) (bias at [K*K])
     int nslots;        // bwd: weight-gradient accumulation slots per CTA
     int raw_plane_bytes;
     int ws_partial_floats;  // bwd: floats of per-chunk partials in the workspace
 };
 
+struct GatherEntry {  // bwd: the (<= 4) destinations d0..d0+n-1 of level l-1 that read source i, with weights
+    int d0, n;
+    float w[4];
+    int pad_[2];
+};
+
 RC_HD int rc_down_size(int n, int k) { return (n + 2 * (k / 2) - k) / 2 + 1; }
 RC_HD int rc_round_up(int v, int m) { return (v + m - 1) / m * m; }
 RC_HD int rc_div_up(int a, int b) { return (a + b - 1) / b; }
+// x / n for 0 <= x < 2^16 by multiplication: magic = floor(2^32 / n) + 1 (n >= 2); magic 0 encodes n == 1
+RC_HD unsigned rc_magic(int n) { return n <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned long long)n) + 1u; }
+RC_HD int rc_fastdiv(int x, unsigned magic) {
+    if (magic == 0u) return x;
+#if defined(__CUDA_ARCH__)
+    return (int)__umulhi((unsigned)x, magic);
+#else
+    return (int)(((unsigned long long)(unsigned)x * magic) >> 32);
+#endif
+}
 
 // window floats loaded per input row by a 4-column strip
 RC_HD int rc_win_s1(int k) { return rc_round_up(kStripW + 2 * (k / 2), 4); }
 RC_HD int rc_win_s2(int k) { return rc_round_up(2 * (kStripW - 1) + k, 4); }
 
-// rows-per-item so that the `g` lanes of a plane are busy and few rounds are needed
+// rows-per-item so that the `g` lanes of a team are busy and few rounds are needed
 RC_H int rc_pick_rpi(int Ho, int Wo, int g, int halo_rows) {
     const int nstrips = rc_div_up(Wo, kStripW);
     int best = 1;
@@ -110,6 +141,8 @@ RC_H int rc_make_plan(Plan& pl, int B, int C, int H, int W, int K, int L, int mo
     int off = 0;
     for (int l = 0; l <= L; ++l) {
         LevelGeo& g = pl.lv[l];
+        g.nstrips = rc_div_up(g.W, kStripW);
+        g.magic_strips = rc_magic(g.nstrips);
         int need = rc_round_up(g.W, kStripW) - kStripW + rc_win_s1(K);  // stride-1 readers of this level
         if (l < L) {  // the stride-2 stencil producing level l+1 reads this level
             const int n2 = 2 * (rc_round_up(pl.lv[l + 1].W, kStripW) - kStripW) + rc_win_s2(K);
@@ -119,15 +152,21 @@ RC_H int rc_make_plan(Plan& pl, int B, int C, int H, int W, int K, int L, int mo
         g.pitch = rc_round_up(need, 4);
         if ((g.pitch & 31) == 0) g.pitch += 4;  // keep row-to-row bank offsets non-zero
         g.rows = g.H + 2 * pad;
+        if (g.rows < pad + 4) g.rows = pad + 4;  // the backward gather reads 4 rows from the interior origin
         if (l < L) {  // stride-2 reader touches rows up to 2*(H_{l+1}-1) + K - 1
             const int r2 = 2 * (pl.lv[l + 1].H - 1) + K;
             if (r2 > g.rows) g.rows = r2;
         }
         g.offS = off; off += g.rows * g.pitch;
         g.offX = g.offGT = g.offGS = -1;
+        if (l >= 1) {
+            g.tpitch = rc_round_up(g.W + 2, 4);
+            g.exact2x = (pl.lv[l - 1].H == 2 * g.H && pl.lv[l - 1].W == 2 * g.W) ? 1 : 0;
+        }
     }
-    const int nT = L >= 1 ? rc_round_up(pl.lv[1].H * pl.lv[1].W, 4) : 0;
-    pl.offT = off; off += nT;
+    int nT = 0;
+    for (int l = 1; l <= L; ++l) { const int n = (pl.lv[l].H + 2) * pl.lv[l].tpitch; if (n > nT) nT = n; }
+    pl.offT = off; off += rc_round_up(nT, 4) + 4;  // + slack: the 2x path may read 3 floats past the last row
     if (backward) {
         for (int l = 1; l <= L; ++l) {
             LevelGeo& g = pl.lv[l];
@@ -137,93 +176,98 @@ RC_H int rc_make_plan(Plan& pl, int B, int C, int H, int W, int K, int L, int mo
         }
         pl.offGY = off; off += pl.lv[0].rows * pl.lv[0].pitch;
         pl.pitchG0 = rc_round_up(W, 4);
-        pl.offG0 = off; off += rc_round_up(H * pl.pitchG0, 4);
+        pl.offG0 = off; off += rc_round_up((H < 4 ? 4 : H) * pl.pitchG0, 4) + 4;
     }
     pl.plane_floats = rc_round_up(off, 4);
-    pl.wstride = K * K + 1;
+    pl.wstride = rc_round_up(K * K + 1, 4);
     pl.raw_plane_bytes = H * W * pl.esize;
+    int vec = 16 / pl.esize;
+    while (vec > 1 && (W % vec) != 0) vec >>= 1;
+    pl.vec = vec;
+    pl.magic_cpr = rc_magic(W / vec);
 
     // table region (shared by all planes of the CTA)
     int tb = 0;
     for (int l = 1; l <= L; ++l) {
         pl.lv[l].tabY = tb; tb += 8 * pl.lv[l - 1].H;
         pl.lv[l].tabX = tb; tb += 8 * pl.lv[l - 1].W;
-        pl.lv[l].rngY = tb; tb += 8 * pl.lv[l].H;
-        pl.lv[l].rngX = tb; tb += 8 * pl.lv[l].W;
+        tb = rc_round_up(tb, 16);
+        if (backward) {
+            pl.lv[l].gatY = tb; tb += (int)sizeof(GatherEntry) * pl.lv[l].H;
+            pl.lv[l].gatX = tb; tb += (int)sizeof(GatherEntry) * pl.lv[l].W;
+        }
     }
     tb = rc_round_up(tb, 16);
 
-    // ---- choose lanes per plane g and planes per CTA P ----
-    const int items0 = rc_div_up(W, kStripW) * H;  // finest split of level 0 (one row per item)
+    // ---- team size g: roughly one lane per 7 rows of a 4-column strip of level 0 ----
+    const int strips0 = rc_div_up(W, kStripW);
     int g = 1;
-    while (g < 32 && g * 2 * 4 <= items0) g *= 2;            // aim at >= ~4 rows per lane ...
-    if (g == 32) { while (g < 256 && (g + 32) * 7 <= items0) g += 32; }  // ... and ~7+ rows per lane for big planes
-    if (g > 32) { int w = g / 32; while (w & (w - 1)) --w; g = w * 32; }  // whole power-of-two warps
+    while (g < kMaxThreads && g * 2 <= strips0 * rc_div_up(H, 7)) g *= 2;
+    if (g * 2 <= kMaxThreads && strips0 * rc_div_up(H, 7) > g + g / 2) g *= 2;  // e.g. 56x56: 112 items -> 128 lanes
     if (opt.force_g) g = opt.force_g;
-    const long per_plane_bytes = (long)pl.plane_floats * 4 + (long)pl.raw_plane_bytes * (backward ? 3 : 2) +
-                                 (long)(L + 2) * pl.wstride * 4;
-    auto smem_for = [&](int P, int T) -> long {
-        const int nslots = backward ? (g >= 32 ? T / 32 : P) : 0;
-        return 64 + tb + per_plane_bytes * P + (long)nslots * (L + 2) * pl.wstride * 4 + 3 * 128 + 256;
+    if (g > kMaxThreads) g = kMaxThreads;
+    const int unit_lanes = g < 32 ? 32 : g;
+    const int ppu = g < 32 ? 32 / g : 1;
+    const int raw_unit = rc_round_up(ppu * pl.raw_plane_bytes, 128);
+    const int n_raw = backward ? 3 : 2;
+    auto smem_for = [&](int units, bool shared_raw) -> long {
+        const int P = units * ppu;
+        const int nslots = backward ? (g >= 32 ? units * (g / 32) : P) : 0;
+        return 128 + tb + (long)P * (L + 2) * pl.wstride * 4 + (long)nslots * (L + 2) * pl.wstride * 4 + 256 +
+               (long)units * raw_unit * (shared_raw ? n_raw - 1 : n_raw) + (long)P * pl.plane_floats * 4;
     };
-    int P = 0;
+    int units = kMaxThreads / unit_lanes;
+    if (units < 1) units = 1;
     if (opt.force_P) {
-        P = opt.force_P;
+        units = rc_div_up(opt.force_P, ppu);
     } else {
-        // target ~128..256 threads per CTA, several CTAs per SM, and 16-byte aligned plane groups for TMA
-        int Pmax = C;
-        const int t_target = g >= 128 ? g : 128;
-        int Pt = t_target / g; if (Pt < 1) Pt = 1;
-        if (Pt > Pmax) Pt = Pmax;
-        P = Pt;
-        // shrink until at least 2 CTAs fit per SM (if possible at all)
-        while (P > 1 && smem_for(P, P * g) * 2 > opt.smem_limit) --P;
-        // prefer a P that divides C and keeps groups 16-byte aligned
-        for (int cand = P; cand >= 1; --cand) {
-            if (C % cand == 0 && ((long)cand * pl.raw_plane_bytes) % 16 == 0) { if (cand * 2 > P) P = cand; break; }
-        }
+        while (units > 1 && units * ppu > rc_round_up(C, ppu)) --units;                   // not more planes than channels
+        while (units > 1 && smem_for(units, false) * 2 > opt.smem_limit) --units;         // >= 2 CTAs per SM if possible
+        // prefer a plane count that divides C (no ragged channel groups, TMA eligible)
+        for (int cand = units; cand >= 1; --cand)
+            if (C % (cand * ppu) == 0) { if (cand * 2 > units) units = cand; break; }
     }
-    if (P < 1) P = 1;
-    if (P > C) P = C;
-    pl.P = P; pl.g = g; pl.T = rc_round_up(P * g, 32);  // whole warps (surplus lanes own no plane)
-    if (pl.T > 1024) return 1;
-    pl.nslots = backward ? (g >= 32 ? pl.T / 32 : P) : 0;
-    pl.n_cg = rc_div_up(C, P);
-    pl.use_tma = (!opt.force_no_tma && C % P == 0 && ((long)P * pl.raw_plane_bytes) % 16 == 0) ? 1 : 0;
+    pl.g = g; pl.unit_lanes = unit_lanes; pl.ppu = ppu; pl.n_units = units;
+    pl.P = units * ppu;
+    pl.T = units * unit_lanes;
+    if (pl.T > kMaxThreads) return 1;
+    pl.nslots = backward ? (g >= 32 ? units * (g / 32) : pl.P) : 0;
+    pl.n_cg = rc_div_up(C, pl.P);
+    pl.use_tma = (!opt.force_no_tma && C % pl.P == 0 && ((long)ppu * pl.raw_plane_bytes) % 16 == 0) ? 1 : 0;
+    pl.share_raw = smem_for(units, false) > opt.smem_limit ? 1 : 0;
+    if (smem_for(units, pl.share_raw != 0) > opt.smem_limit) return 1;
 
-    // rows per item on every level
     for (int l = 0; l <= L; ++l) {
         pl.lv[l].rpi = rc_pick_rpi(pl.lv[l].H, pl.lv[l].W, g, K - 1);
         pl.lv[l].rpi_down = l >= 1 ? rc_pick_rpi(pl.lv[l].H, pl.lv[l].W, g, K - 2) : 0;
+        pl.lv[l].rpu = l >= 1 ? rc_pick_rpi(pl.lv[l].H, pl.lv[l - 1].W, g, 1) : 0;
+        pl.lv[l].magic_W = rc_magic(pl.lv[l].W);
     }
 
     // shared memory map
-    int sm = 64;  // two mbarriers + padding
+    int sm = 0;
+    pl.smBar = sm; sm += 128;  // one mbarrier per unit (<= 8 units)
     pl.smTab = sm; sm += tb;
-    pl.smW = sm; sm += P * (L + 2) * pl.wstride * 4;
+    pl.smW = sm; sm += pl.P * (L + 2) * pl.wstride * 4;
     pl.smWG = sm; sm += pl.nslots * (L + 2) * pl.wstride * 4;
     sm = rc_round_up(sm, 128);
-    pl.smRawX = sm; sm += rc_round_up(P * pl.raw_plane_bytes, 128);
-    pl.smRawG = sm; if (backward) sm += rc_round_up(P * pl.raw_plane_bytes, 128);
-    pl.smRawOut = sm; sm += rc_round_up(P * pl.raw_plane_bytes, 128);
-    pl.smPlanes = sm; sm += P * pl.plane_floats * 4;
-    if (sm > opt.smem_limit) {  // big planes: write the result over a raw input buffer that is dead by then
-        pl.share_raw = 1;
-        const int raw = rc_round_up(P * pl.raw_plane_bytes, 128);
-        pl.smRawOut = backward ? pl.smRawG : pl.smRawX;
-        pl.smPlanes -= raw; sm -= raw;
-    }
+    pl.raw_unit_bytes = raw_unit;
+    pl.smRawX = sm; sm += units * raw_unit;
+    pl.smRawG = sm; if (backward) sm += units * raw_unit;
+    if (pl.share_raw) pl.smRawOut = backward ? pl.smRawG : pl.smRawX;
+    else { pl.smRawOut = sm; sm += units * raw_unit; }
+    pl.smPlanes = sm; sm += pl.P * pl.plane_floats * 4;
     pl.smem_bytes = sm;
     if (sm > opt.smem_limit) return 1;
 
-    // grid: enough CTAs for a few waves, but never more chunks than images
+    // grid: enough CTAs for a full wave of resident CTAs, never more chunks than images
     int ctas_per_sm = opt.smem_limit / (sm + 1024);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int max_by_threads = 2048 / pl.T > 0 ? 2048 / pl.T : 1;
     if (ctas_per_sm > max_by_threads) ctas_per_sm = max_by_threads;
     if (ctas_per_sm > 32) ctas_per_sm = 32;
     const long resident = (long)opt.num_sms * ctas_per_sm;
-    int n_chunk = (int)((resident * (backward ? 1 : 2) + pl.n_cg - 1) / pl.n_cg);
+    int n_chunk = (int)(resident / pl.n_cg);  // each CTA loops over its chunk of images
     if (n_chunk > B) n_chunk = B;
     if (n_chunk < 1) n_chunk = 1;
     if (opt.force_chunks) n_chunk = opt.force_chunks > B ? B : opt.force_chunks;

@@ -21,7 +21,6 @@
 namespace recnext {
 
 struct IdxLam { int i0; float lam; };
-struct Range { int lo, hi; };
 
 // ---------------------------------------------------------------------------------------------------------
 // interpolation source indices — bit-exact contract with ATen.
@@ -93,32 +92,59 @@ RC_HD void rc_load_row(float (&dst)[N], const float* __restrict__ src) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Stage: raw plane group (element type T, unpadded, planes back to back) -> padded fp32 interiors.
-// Flat over all threads of the CTA (any thread may touch any plane).
+// Stage: raw planes of one unit (element type T, unpadded, planes back to back) -> padded fp32 interiors.
+// Rows are cut into chunks of V elements (V = largest power of two dividing W, <= 16 bytes), so every chunk is
+// one aligned vector load and never straddles a row.  `nl` lanes of the unit share the chunks.
 // ---------------------------------------------------------------------------------------------------------
-template <typename T>
-RC_HD void rc_unpack_group(const T* __restrict__ raw, int nplanes, int H, int W, float* __restrict__ planes,
-                           int plane_floats, int off, int pitch, int pad, int tid, int nthreads) {
-    constexpr int V = 16 / (int)sizeof(T);
-    const int HW = H * W, total = nplanes * HW;
-    for (int v = tid; v * V < total; v += nthreads) {
-        const int idx = v * V;
-        int q = idx / HW;
-        const int rem = idx - q * HW;
-        int i = rem / W, j = rem - i * W;
+template <typename T, int V>
+RC_HD void rc_unpack_rows(const T* __restrict__ raw, int nrows_total, int H, int W, unsigned magic_cpr, unsigned magic_H,
+                          float* __restrict__ planes, int plane_floats, int off, int pitch, int pad, int lane, int nl) {
+    const int cpr = W / V;
+    const int nchunks = nrows_total * cpr;
+    for (int ci = lane; ci < nchunks; ci += nl) {
+        const int r = rc_fastdiv(ci, magic_cpr);       // row within the unit (plane-major)
+        const int col = (ci - r * cpr) * V;
+        const int q = rc_fastdiv(r, magic_H);          // plane within the unit
+        const int i = r - q * H;
         alignas(16) T vals[V];
-        *reinterpret_cast<float4*>(vals) = *reinterpret_cast<const float4*>(raw + idx);  // buffers are 128-B padded
-        float* dst = planes + (long)q * plane_floats + off + (i + pad) * pitch + pad;
+        if (V * sizeof(T) == 16) *reinterpret_cast<float4*>(vals) = *reinterpret_cast<const float4*>(raw + (long)r * W + col);
+        else if (V * sizeof(T) == 8) *reinterpret_cast<float2*>(vals) = *reinterpret_cast<const float2*>(raw + (long)r * W + col);
+        else if (V * sizeof(T) == 4) *reinterpret_cast<float*>(vals) = *reinterpret_cast<const float*>(raw + (long)r * W + col);
+        else vals[0] = raw[(long)r * W + col];
+        float* dst = planes + (long)q * plane_floats + off + (i + pad) * pitch + pad + col;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            if (idx + e < total) {
-                dst[j] = Elem<T>::to_f(vals[e]);
-                if (++j == W) {
-                    j = 0; dst += pitch;
-                    if (++i == H) { i = 0; ++q; dst = planes + (long)q * plane_floats + off + pad * pitch + pad; }
-                }
-            }
-        }
+        for (int e = 0; e < V; ++e) dst[e] = Elem<T>::to_f(vals[e]);
+    }
+}
+
+template <typename T>
+RC_HD void rc_unpack_unit(const T* raw, int nplanes, int H, int W, int vec, unsigned magic_cpr, unsigned magic_H, float* planes,
+                          int plane_floats, int off, int pitch, int pad, int lane, int nl) {
+    const int rows = nplanes * H;
+    switch (vec * (int)sizeof(T)) {
+        case 16: rc_unpack_rows<T, 16 / (int)sizeof(T)>(raw, rows, H, W, magic_cpr, magic_H, planes, plane_floats, off, pitch, pad, lane, nl); break;
+        case 8: rc_unpack_rows<T, 8 / (int)sizeof(T)>(raw, rows, H, W, magic_cpr, magic_H, planes, plane_floats, off, pitch, pad, lane, nl); break;
+        case 4: rc_unpack_rows<T, 4 / (int)sizeof(T)>(raw, rows, H, W, magic_cpr, magic_H, planes, plane_floats, off, pitch, pad, lane, nl); break;
+        default: rc_unpack_rows<T, 1>(raw, rows, H, W, magic_cpr, magic_H, planes, plane_floats, off, pitch, pad, lane, nl); break;
+    }
+}
+
+template <int N>
+RC_HD void rc_load_filter(float (&w)[N], const float* __restrict__ wsm, bool flip) {
+    // wsm slots are 16-byte aligned and padded to a multiple of 4 floats (plan.wstride)
+    constexpr int N4 = (N + 3) / 4;
+    float tmp[N4 * 4];
+#pragma unroll
+    for (int q = 0; q < N4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(wsm + 4 * q);
+        tmp[4 * q + 0] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w;
+    }
+    if (flip) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = tmp[N - 1 - i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = tmp[i];
     }
 }
 
@@ -128,17 +154,16 @@ RC_HD void rc_unpack_group(const T* __restrict__ raw, int nplanes, int H, int W,
 // ---------------------------------------------------------------------------------------------------------
 template <int K, bool FLIP, class Epi>
 RC_HD void rc_conv_s1(const float* __restrict__ src, int pitch, const float* __restrict__ wsm, bool use_bias, int Ho,
-                      int Wo, int rpi, int lane, int g, Epi epi) {
+                      int Wo, unsigned magic_strips, int rpi, int lane, int g, Epi epi) {
     constexpr int WL = (kStripW + 2 * (K / 2) + 3) & ~3;
     const int nstrips = (Wo + kStripW - 1) / kStripW;
     const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
     if (lane >= nitems) return;
     float w[K * K];
-#pragma unroll
-    for (int i = 0; i < K * K; ++i) w[i] = FLIP ? wsm[K * K - 1 - i] : wsm[i];
+    rc_load_filter<K * K>(w, wsm, FLIP);
     const float bias = use_bias ? wsm[K * K] : 0.f;
     for (int item = lane; item < nitems; item += g) {
-        const int rb = item / nstrips, st = item - rb * nstrips;
+        const int rb = rc_fastdiv(item, magic_strips), st = item - rb * nstrips;
         const int r0 = rb * rpi, c0 = st * kStripW;
         const int nrows = (Ho - r0) < rpi ? (Ho - r0) : rpi;
         const float* base = src + r0 * pitch + c0;
@@ -167,17 +192,16 @@ RC_HD void rc_conv_s1(const float* __restrict__ src, int pitch, const float* __r
 // Stage: depthwise KxK STRIDE-2 cross-correlation (the shared `down` filter): level l-1 (padded) -> level l.
 template <int K, class Epi>
 RC_HD void rc_conv_s2(const float* __restrict__ src, int pitch, const float* __restrict__ wsm, bool use_bias, int Ho,
-                      int Wo, int rpi, int lane, int g, Epi epi) {
+                      int Wo, unsigned magic_strips, int rpi, int lane, int g, Epi epi) {
     constexpr int WL = (2 * (kStripW - 1) + K + 3) & ~3;
     const int nstrips = (Wo + kStripW - 1) / kStripW;
     const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
     if (lane >= nitems) return;
     float w[K * K];
-#pragma unroll
-    for (int i = 0; i < K * K; ++i) w[i] = wsm[i];
+    rc_load_filter<K * K>(w, wsm, false);
     const float bias = use_bias ? wsm[K * K] : 0.f;
     for (int item = lane; item < nitems; item += g) {
-        const int rb = item / nstrips, st = item - rb * nstrips;
+        const int rb = rc_fastdiv(item, magic_strips), st = item - rb * nstrips;
         const int r0 = rb * rpi, c0 = st * kStripW;
         const int nrows = (Ho - r0) < rpi ? (Ho - r0) : rpi;
         const float* base = src + 2 * r0 * pitch + 2 * c0;
@@ -207,70 +231,150 @@ RC_HD void rc_conv_s2(const float* __restrict__ src, int pitch, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Stage: s_{l-1} = x_{l-1} + interpolate(t_l, size = level l-1)   (model/recnext.py:33, the `f + x` of the
-// next iteration folded in).  T is unpadded [Hl x Wl]; dst is the padded level l-1 buffer, updated in place.
+// T buffer: the conv output t_l awaiting interpolation, (Hl+2) x tpitch floats with the interior at (+1,+1)
+// and a REPLICATE border of one pixel.  With that border the exact-2x bilinear case of F.interpolate
+// (align_corners=False) is the fixed 0.25/0.75 stencil, including ATen's clamping at the image edges.
 // ---------------------------------------------------------------------------------------------------------
-RC_HD void rc_upsample_add(float* __restrict__ dstS, int pitch, int pad, int Hd, int Wd, const float* __restrict__ T,
-                           int Hl, int Wl, const IdxLam* __restrict__ ytab, const IdxLam* __restrict__ xtab, int mode,
-                           int lane, int g) {
-    const int nstrips = (Wd + kStripW - 1) / kStripW;
-    const int nitems = nstrips * Hd;
+RC_HD void rc_store_T(float* __restrict__ T, int tp, int Hl, int Wl, int row, int c0, const float (&v)[kStripW]) {
+    float* r = T + (row + 1) * tp + 1 + c0;
+    const int last = Wl - 1 - c0;  // 0..3 if this strip holds the last column
+    const float vl = last == 0 ? v[0] : (last == 1 ? v[1] : (last == 2 ? v[2] : v[3]));
+    const bool top = row == 0, bot = row == Hl - 1;
+#pragma unroll
+    for (int c = 0; c < kStripW; ++c)
+        if (c0 + c < Wl) {
+            r[c] = v[c];
+            if (top) r[c - tp] = v[c];
+            if (bot) r[c + tp] = v[c];
+        }
+    if (c0 == 0) {
+        r[-1] = v[0];
+        if (top) r[-1 - tp] = v[0];
+        if (bot) r[-1 + tp] = v[0];
+    }
+    if (last >= 0 && last < kStripW) {
+        r[last + 1] = vl;
+        if (top) r[last + 1 - tp] = vl;
+        if (bot) r[last + 1 + tp] = vl;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stage: s_{l-1} = x_{l-1} + interpolate(t_l, size = level l-1)   (model/recnext.py:33, with the `f + x` of the
+// next loop iteration folded in).  dstS is the padded level l-1 buffer, updated in place.
+// Fast path: both dimensions exactly 2x, bilinear.  Items = (4 output columns) x (rpu source rows).
+// ---------------------------------------------------------------------------------------------------------
+RC_HD void rc_hinterp2x(float (&h)[kStripW], const float* __restrict__ trow) {
+    // trow points at padded column m0 (= source column m0 - 1); m0 is even, so two aligned float2 loads
+    const float2 a = *reinterpret_cast<const float2*>(trow);
+    const float2 b = *reinterpret_cast<const float2*>(trow + 2);
+    h[0] = 0.75f * a.y + 0.25f * a.x;
+    h[1] = 0.75f * a.y + 0.25f * b.x;
+    h[2] = 0.75f * b.x + 0.25f * a.y;
+    h[3] = 0.75f * b.x + 0.25f * b.y;
+}
+
+RC_HD void rc_upsample2x_add(float* __restrict__ dstS, int pitch, int pad, int Hd, int Wd, const float* __restrict__ T, int tp,
+                             int Hl, unsigned magic_strips, int nstrips, int rpu, int lane, int g) {
+    const int nitems = nstrips * ((Hl + rpu - 1) / rpu);
     for (int item = lane; item < nitems; item += g) {
-        const int i = item / nstrips, c0 = (item - i * nstrips) * kStripW;
-        const IdxLam ty = ytab[i];
-        float* d = dstS + (i + pad) * pitch + pad;
-        if (mode == 1) {
-            const float* t0 = T + ty.i0 * Wl;
+        const int rb = rc_fastdiv(item, magic_strips), q = item - rb * nstrips;
+        const int m_begin = rb * rpu;
+        const int m_end = (m_begin + rpu) < Hl ? (m_begin + rpu) : Hl;
+        const int j0 = q * kStripW;
+        const float* tcol = T + 2 * q;  // padded column index of source column 2q - 1
+        float hp[kStripW], hc[kStripW], hn[kStripW];
+        rc_hinterp2x(hp, tcol + (m_begin) * tp);      // source row m_begin - 1 (padded row m_begin)
+        rc_hinterp2x(hc, tcol + (m_begin + 1) * tp);  // source row m_begin
+        float* d = dstS + (2 * m_begin + pad) * pitch + pad + j0;
+        for (int m = m_begin; m < m_end; ++m) {
+            rc_hinterp2x(hn, tcol + (m + 2) * tp);    // source row m + 1
+            if (((pad | pitch) & 1) == 0 && j0 + kStripW <= Wd) {  // aligned float2 read-modify-write
 #pragma unroll
-            for (int c = 0; c < kStripW; ++c) {
-                const int j = c0 + c;
-                if (j < Wd) d[j] += t0[xtab[j].i0];
-            }
-        } else {
-            const int y1 = ty.i0 + (ty.i0 < Hl - 1 ? 1 : 0);
-            const float ly = ty.lam, hy = 1.f - ly;
-            const float* t0 = T + ty.i0 * Wl;
-            const float* t1 = T + y1 * Wl;
-#pragma unroll
-            for (int c = 0; c < kStripW; ++c) {
-                const int j = c0 + c;
-                if (j < Wd) {
-                    const IdxLam tx = xtab[j];
-                    const int x1 = tx.i0 + (tx.i0 < Wl - 1 ? 1 : 0);
-                    const float lx = tx.lam, hx = 1.f - lx;
-                    const float v = hy * (hx * t0[tx.i0] + lx * t0[x1]) + ly * (hx * t1[tx.i0] + lx * t1[x1]);
-                    d[j] += v;
+                for (int rr = 0; rr < 2; ++rr) {
+                    const float (&ho)[kStripW] = rr ? hn : hp;
+                    float2* d2 = reinterpret_cast<float2*>(d + rr * pitch);
+                    float2 u = d2[0], v = d2[1];
+                    u.x += 0.75f * hc[0] + 0.25f * ho[0]; u.y += 0.75f * hc[1] + 0.25f * ho[1];
+                    v.x += 0.75f * hc[2] + 0.25f * ho[2]; v.y += 0.75f * hc[3] + 0.25f * ho[3];
+                    d2[0] = u; d2[1] = v;
                 }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kStripW; ++c)
+                    if (j0 + c < Wd) {
+                        d[c] += 0.75f * hc[c] + 0.25f * hp[c];          // output row 2m
+                        d[pitch + c] += 0.75f * hc[c] + 0.25f * hn[c];  // output row 2m + 1
+                    }
+            }
+            d += 2 * pitch;
+#pragma unroll
+            for (int c = 0; c < kStripW; ++c) { hp[c] = hc[c]; hc[c] = hn[c]; }
+        }
+    }
+}
+
+// Generic path (odd sizes such as 7 -> 4, nearest mode): table driven.  Items = 4 columns x rpi rows of level l-1.
+RC_HD void rc_upsample_add(float* __restrict__ dstS, int pitch, int pad, int Hd, int Wd, const float* __restrict__ T, int tp,
+                           int Hl, int Wl, const IdxLam* __restrict__ ytab, const IdxLam* __restrict__ xtab, int mode,
+                           unsigned magic_strips, int nstrips, int rpi, int lane, int g) {
+    const int nitems = nstrips * ((Hd + rpi - 1) / rpi);
+    for (int item = lane; item < nitems; item += g) {
+        const int rb = rc_fastdiv(item, magic_strips), q = item - rb * nstrips;
+        const int j0 = q * kStripW;
+        const int i_end = (rb * rpi + rpi) < Hd ? (rb * rpi + rpi) : Hd;
+        int x0[kStripW], x1[kStripW];
+        float lx[kStripW];
+#pragma unroll
+        for (int c = 0; c < kStripW; ++c) {
+            const int j = (j0 + c) < Wd ? (j0 + c) : (Wd - 1);
+            const IdxLam t = xtab[j];
+            x0[c] = t.i0 + 1;  // +1: T interior starts at padded column 1
+            x1[c] = (mode == 1) ? x0[c] : t.i0 + (t.i0 < Wl - 1 ? 1 : 0) + 1;
+            lx[c] = t.lam;
+        }
+        for (int i = rb * rpi; i < i_end; ++i) {
+            const IdxLam ty = ytab[i];
+            float* d = dstS + (i + pad) * pitch + pad + j0;
+            const float* t0 = T + (ty.i0 + 1) * tp;
+            if (mode == 1) {
+#pragma unroll
+                for (int c = 0; c < kStripW; ++c)
+                    if (j0 + c < Wd) d[c] += t0[x0[c]];
+            } else {
+                const float* t1 = T + (ty.i0 + (ty.i0 < Hl - 1 ? 1 : 0) + 1) * tp;
+                const float ly = ty.lam, hy = 1.f - ly;
+#pragma unroll
+                for (int c = 0; c < kStripW; ++c)
+                    if (j0 + c < Wd) {
+                        const float hx = 1.f - lx[c];
+                        d[c] += hy * (hx * t0[x0[c]] + lx[c] * t0[x1[c]]) + ly * (hx * t1[x0[c]] + lx[c] * t1[x1[c]]);
+                    }
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Stage (bwd): transpose of the interpolation as a GATHER (deterministic): for every source pixel of level l
-// sum the destinations of level l-1 that read it.  rng tables give the contiguous destination ranges.
-// gsrc points at the INTERIOR origin of the level l-1 gradient (pitch gpitch); dst is the padded GT_l buffer.
+// Stage (bwd): transpose of the interpolation as a GATHER (deterministic): every source pixel of level l sums
+// the (<= 4 x 4) destinations of level l-1 that read it, with the weights tabulated once per CTA.
+// gsrc points at the INTERIOR origin of the level l-1 gradient (pitch gpitch; reads may run up to 3 elements
+// past a row / the last row — those cells are finite and carry weight 0).  dst is the padded GT_l buffer.
 // ---------------------------------------------------------------------------------------------------------
-RC_HD float rc_interp_weight(const IdxLam t, int src, int in_size, int mode) {
-    if (mode == 1) return t.i0 == src ? 1.f : 0.f;
-    const int i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
-    return (t.i0 == src ? 1.f - t.lam : 0.f) + (i1 == src ? t.lam : 0.f);
-}
-
 RC_HD void rc_upsample_bwd(float* __restrict__ dstGT, int pitch, int pad, int Hl, int Wl, const float* __restrict__ gsrc,
-                           int gpitch, const IdxLam* __restrict__ ytab, const IdxLam* __restrict__ xtab,
-                           const Range* __restrict__ yr, const Range* __restrict__ xr, int mode, int lane, int g) {
+                           int gpitch, const GatherEntry* __restrict__ gy, const GatherEntry* __restrict__ gx,
+                           unsigned magic_W, int lane, int g) {
     const int n = Hl * Wl;
     for (int idx = lane; idx < n; idx += g) {
-        const int iy = idx / Wl, ix = idx - iy * Wl;
-        const Range ry = yr[iy], rx = xr[ix];
+        const int iy = rc_fastdiv(idx, magic_W), ix = idx - iy * Wl;
+        const GatherEntry ey = gy[iy], ex = gx[ix];
+        const float* p = gsrc + ey.d0 * gpitch + ex.d0;
         float acc = 0.f;
-        for (int dy = ry.lo; dy <= ry.hi; ++dy) {
-            const float wy = rc_interp_weight(ytab[dy], iy, Hl, mode);
-            const float* grow = gsrc + dy * gpitch;
-            float rowacc = 0.f;
-            for (int dx = rx.lo; dx <= rx.hi; ++dx) rowacc = fmaf(rc_interp_weight(xtab[dx], ix, Wl, mode), grow[dx], rowacc);
-            acc = fmaf(wy, rowacc, acc);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float* row = p + a * gpitch;
+            const float r = ex.w[0] * row[0] + ex.w[1] * row[1] + ex.w[2] * row[2] + ex.w[3] * row[3];
+            acc = fmaf(ey.w[a], r, acc);
         }
         dstGT[(iy + pad) * pitch + ix + pad] = acc;
     }
@@ -281,14 +385,14 @@ RC_HD void rc_upsample_bwd(float* __restrict__ dstGT, int pitch, int pad, int Hl
 // lane's items; acc[K*K] += sum G (bias gradient).  S and G are padded buffers of the same level geometry.
 // ---------------------------------------------------------------------------------------------------------
 template <int K>
-RC_HD void rc_wgrad_s1(const float* __restrict__ S, const float* __restrict__ G, int pitch, int Ho, int Wo, int rpi,
-                       int lane, int g, float (&acc)[K * K + 1]) {
+RC_HD void rc_wgrad_s1(const float* __restrict__ S, const float* __restrict__ G, int pitch, int Ho, int Wo,
+                       unsigned magic_strips, int rpi, int lane, int g, float (&acc)[K * K + 1]) {
     constexpr int WL = (kStripW + 2 * (K / 2) + 3) & ~3;
     constexpr int PAD = K / 2;
     const int nstrips = (Wo + kStripW - 1) / kStripW;
     const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
     for (int item = lane; item < nitems; item += g) {
-        const int rb = item / nstrips, st = item - rb * nstrips;
+        const int rb = rc_fastdiv(item, magic_strips), st = item - rb * nstrips;
         const int r0 = rb * rpi, c0 = st * kStripW;
         const int nrows = (Ho - r0) < rpi ? (Ho - r0) : rpi;
         const float* base = S + r0 * pitch + c0;
@@ -321,13 +425,13 @@ RC_HD void rc_wgrad_s1(const float* __restrict__ S, const float* __restrict__ G,
 // Weight gradient of the stride-2 `down` conv: X = padded level l-1 input, G = padded total gradient of x_l.
 template <int K>
 RC_HD void rc_wgrad_s2(const float* __restrict__ X, int xpitch, const float* __restrict__ G, int gpitch, int Ho, int Wo,
-                       int rpi, int lane, int g, float (&acc)[K * K + 1]) {
+                       unsigned magic_strips, int rpi, int lane, int g, float (&acc)[K * K + 1]) {
     constexpr int WL = (2 * (kStripW - 1) + K + 3) & ~3;
     constexpr int PAD = K / 2;
     const int nstrips = (Wo + kStripW - 1) / kStripW;
     const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
     for (int item = lane; item < nitems; item += g) {
-        const int rb = item / nstrips, st = item - rb * nstrips;
+        const int rb = rc_fastdiv(item, magic_strips), st = item - rb * nstrips;
         const int r0 = rb * rpi, c0 = st * kStripW;
         const int nrows = (Ho - r0) < rpi ? (Ho - r0) : rpi;
         const float* base = X + 2 * r0 * xpitch + 2 * c0;
@@ -374,8 +478,7 @@ RC_HD void rc_convT_s2(const float* __restrict__ G, int gpitch, const float* __r
     const int nitems = na * nb;
     if (lane >= nitems) return;
     float w[K * K];
-#pragma unroll
-    for (int i = 0; i < K * K; ++i) w[i] = wsm[i];
+    rc_load_filter<K * K>(w, wsm, false);
     for (int item = lane; item < nitems; item += g) {
         const int a = item / nb, b = item - a * nb;
         float gw[NW][NW];
@@ -416,16 +519,41 @@ RC_HD void rc_build_fwd_table(IdxLam* tab, int in_size, int out_size, int mode, 
         tab[d] = t;
     }
 }
-RC_HD void rc_build_range_table(Range* rng, const IdxLam* tab, int in_size, int out_size, int mode, int tid, int nthreads) {
+// bwd: for every source index s of level l, the destinations d0..d0+n-1 (n <= 4 because out <= 2*in) of level
+// l-1 whose interpolation reads s, and the weight each of them gives to s.  Returns false if n > 4.
+RC_HD void rc_build_gather_table(GatherEntry* gat, const IdxLam* tab, int in_size, int out_size, int mode, int tid, int nthreads) {
     for (int s = tid; s < in_size; s += nthreads) {
-        Range r; r.lo = 0; r.hi = -1;
+        GatherEntry e;
+        e.d0 = 0; e.n = 0; e.w[0] = e.w[1] = e.w[2] = e.w[3] = 0.f; e.pad_[0] = e.pad_[1] = 0;
         bool found = false;
         for (int d = 0; d < out_size; ++d) {
             const int i0 = tab[d].i0;
             const int i1 = mode == 1 ? i0 : i0 + (i0 < in_size - 1 ? 1 : 0);
-            if (i0 == s || i1 == s) { if (!found) { r.lo = d; found = true; } r.hi = d; }
+            const float w = mode == 1 ? (i0 == s ? 1.f : 0.f) : ((i0 == s ? 1.f - tab[d].lam : 0.f) + (i1 == s ? tab[d].lam : 0.f));
+            if (w != 0.f) {  // (a destination whose lambda is exactly 0 reads i1 with weight 0: not a reader)
+                if (!found) { e.d0 = d; found = true; }
+                const int k = d - e.d0;
+                if (k < 4) {
+                    if (k == 0) e.w[0] = w; else if (k == 1) e.w[1] = w; else if (k == 2) e.w[2] = w; else e.w[3] = w;
+                }
+                e.n = k + 1;
+            }
         }
-        rng[s] = r;
+        // all four reads d0..d0+3 must stay inside the level (or inside the 4-row/col minimum the plan allocates)
+        const int limit = out_size >= 4 ? out_size - 4 : 0;
+        if (e.d0 > limit) {
+            const int sh = e.d0 - limit;  // 1..3
+            float w4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float wk = k == 0 ? e.w[0] : (k == 1 ? e.w[1] : (k == 2 ? e.w[2] : e.w[3]));
+                const int t = k + sh;
+                if (t == 1) w4[1] = wk; else if (t == 2) w4[2] = wk; else if (t == 3) w4[3] = wk;
+            }
+            e.w[0] = w4[0]; e.w[1] = w4[1]; e.w[2] = w4[2]; e.w[3] = w4[3];
+            e.d0 = limit;
+        }
+        gat[s] = e;
     }
 }
 

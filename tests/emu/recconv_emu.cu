@@ -18,15 +18,26 @@
 using namespace recnext;
 
 struct HostCtx {
-    int T;
+    int T, n_units;
     template <class F> __host__ __device__ void run(F f) { for (int t = 0; t < T; ++t) f(t); }
     __host__ __device__ void sync() {}
-    __host__ __device__ void load_begin(void* d0, const void* s0, long b0, void* d1, const void* s1, long b1) {
-        memcpy(d0, s0, b0);
-        if (b1) memcpy(d1, s1, b1);
+    __host__ __device__ void cta_sync() {}
+    template <class F> __host__ __device__ void load_begin(F desc) {
+        for (int u = 0; u < n_units; ++u) {
+            void *d0, *d1; const void *s0, *s1; long b0, b1;
+            desc(u, d0, s0, b0, d1, s1, b1);
+            if (b0) memcpy(d0, s0, b0);
+            if (b1) memcpy(d1, s1, b1);
+        }
     }
     __host__ __device__ void load_wait() {}
-    __host__ __device__ void store(void* dst, const void* src, long bytes) { memcpy(dst, src, bytes); }
+    template <class F> __host__ __device__ void store(F desc) {
+        for (int u = 0; u < n_units; ++u) {
+            void* dst; const void* src; long bytes;
+            desc(u, dst, src, bytes);
+            if (bytes) memcpy(dst, src, bytes);
+        }
+    }
     __host__ __device__ void store_drain() {}
     template <int N> __host__ __device__ void wgrad_commit(const ThreadPos& t, const Plan& pl, float (&acc)[N], float* slot) {
         if (t.p < pl.P) for (int i = 0; i < N; ++i) slot[i] += acc[i];
@@ -40,7 +51,7 @@ static void run_all(const Plan& pl, const KernelArgs& a, bool bwd) {
     for (int blk = 0; blk < pl.n_cg * pl.n_chunk; ++blk) {
         // poison shared memory so that reads of never-written (non-zeroed) cells show up as NaN
         memset(smem, 0xff, pl.smem_bytes);
-        HostCtx ctx{pl.T};
+        HostCtx ctx{pl.T, pl.n_units};
         const int cg = blk % pl.n_cg, chunk = blk / pl.n_cg;
         if (bwd) rc_backward_body<K, T>(ctx, pl, a, smem, cg, chunk);
         else rc_forward_body<K, T>(ctx, pl, a, smem, cg, chunk);
@@ -82,13 +93,13 @@ int emu_recconv(const recconv_desc* d, const recconv_params* p, const void* x, c
         default: return -2;
     }
     if (backward) {
-        const int KK = d->k * d->k, ws = KK + 1;
+        const int KK = d->k * d->k, ws = pl.wstride;
         const long total = (long)(d->level + 2) * d->C * ws;
         for (long i = 0; i < total; ++i) {
             float s = 0.f;
             for (int ch = 0; ch < pl.n_chunk; ++ch) s += partial[(size_t)ch * total + i];
             const long sc = i / ws; const int e = (int)(i - sc * ws);
-            if (e < KK) gw[sc * KK + e] = s; else if (gb) gb[sc] = s;
+            if (e < KK) gw[sc * KK + e] = s; else if (e == KK && gb) gb[sc] = s;
         }
     }
     return 0;
