@@ -190,7 +190,7 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
                      backward ? "bwd" : "fwd", pl.K, pl.L, pl.B, pl.C, pl.H, pl.W, pl.P, pl.g, pl.n_units, pl.T, pl.n_cg, pl.n_chunk,
                      pl.img_per_chunk, pl.smem_bytes, pl.plane_floats * 4, pl.use_tma, pl.share_raw);
     for (int l = 0; l <= pl.L && n > 0 && (size_t)n < buflen; ++l)
-        n += snprintf(buf + n, buflen - n, "%s%d/%d", l ? "," : "", pl.lv[l].rpi, pl.lv[l].rpi_down);
+        n += snprintf(buf + n, buflen - n, "%s%d/%d(%d)", l ? "," : "", pl.lv[l].g1.rpi, pl.lv[l].g2.rpi, pl.lv[l].g1.lanes);
     return RECNEXT_OK;
 }
 

@@ -1,8 +1,9 @@
 // recconv_body.cuh — stage schedules of the fused RecConv forward / backward kernels.
 //
 // The schedule is a template over an execution context `Ctx`:
-//   ctx.run(f)            f(tid) for every thread of the CTA (device: this thread; host emulation: a loop)
-//   ctx.sync()            TEAM / UNIT barrier (device: __syncwarp or a named barrier; teams never interact)
+//   ctx.run(n, f)         f(pos) for every thread whose lane-in-unit is < n (device: this thread; host: a loop)
+//   ctx.sync(n)           barrier among the first n lanes of each unit (device: __syncwarp or a named barrier;
+//                         units never interact).  A stage that needs few lanes is skipped by the other warps.
 //   ctx.cta_sync()        whole-CTA barrier (prologue and epilogue only)
 //   ctx.load_begin / load_wait / store / store_drain   movement of one unit's raw planes (TMA bulk copies)
 //   ctx.wgrad_commit      reduction of per-lane weight-gradient partials into the CTA's accumulation slots
@@ -71,7 +72,7 @@ RC_HD UnitIO rc_unit_io(const Plan& pl, unsigned char* smem, int cg, int u) {
 template <class Ctx>
 RC_HD void rc_prologue(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsigned char* smem, int cg) {
     const int nact = (pl.C - cg * pl.P) < pl.P ? (pl.C - cg * pl.P) : pl.P;
-    ctx.run([&](int tid) {
+    ctx.run_all([&](int tid) {
         // zero every plane block (borders must stay zero for the whole kernel) and the accumulation slots
         float4* z = reinterpret_cast<float4*>(smem + pl.smPlanes);
         const int n4 = pl.P * pl.plane_floats / 4;
@@ -104,7 +105,7 @@ RC_HD void rc_prologue(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsigned c
     });
     ctx.cta_sync();
     if (pl.backward) {
-        ctx.run([&](int tid) {
+        ctx.run_all([&](int tid) {
             for (int l = 1; l <= pl.L; ++l) {
                 rc_build_gather_table(reinterpret_cast<GatherEntry*>(smem + pl.smTab + pl.lv[l].gatY),
                                       reinterpret_cast<const IdxLam*>(smem + pl.smTab + pl.lv[l].tabY), pl.lv[l].H,
@@ -122,8 +123,7 @@ template <typename T, class Ctx>
 RC_HD void rc_unpack_stage(Ctx& ctx, const Plan& pl, unsigned char* smem, int cg, bool from_g, int off_dst) {
     const int PAD = pl.K / 2;
     const unsigned magic_H = rc_magic(pl.H);
-    ctx.run([&](int tid) {
-        const ThreadPos t = rc_thread_pos(pl, tid, cg);
+    ctx.run(pl.unit_lanes, [&](const ThreadPos& t) {
         const UnitIO io = rc_unit_io<T>(pl, smem, cg, t.u);
         if (io.nact == 0) return;
         float* planes = reinterpret_cast<float*>(smem + pl.smPlanes) + (long)t.u * pl.ppu * pl.plane_floats;
@@ -132,15 +132,29 @@ RC_HD void rc_unpack_stage(Ctx& ctx, const Plan& pl, unsigned char* smem, int cg
     });
 }
 
+// Stage sequencing inside a unit: before a stage that uses the first n lanes, the first max(previous n, n) lanes
+// synchronise, so warps that are not needed skip both the stage and its barriers.
+struct StageSeq {
+    int prev;
+    template <class Ctx, class F> RC_HD void stage(Ctx& ctx, int n, F f) {
+        ctx.sync(prev > n ? prev : n);
+        ctx.run(n, f);
+        prev = n;
+    }
+    template <class Ctx> RC_HD void join(Ctx& ctx, int n) {  // barrier only (before a unit-wide operation)
+        ctx.sync(prev > n ? prev : n);
+        prev = n;
+    }
+};
+
 // The recompute shared by forward and backward: S_l for all levels (s_l = x_l + u_l), optionally keeping x_l.
 template <int K, class Ctx>
-RC_HD void rc_pyramid(Ctx& ctx, const Plan& pl, unsigned char* smem, int cg, bool keep_x) {
+RC_HD void rc_pyramid(Ctx& ctx, StageSeq& seq, const Plan& pl, unsigned char* smem, bool keep_x) {
     constexpr int PAD = K / 2;
     float* planes = reinterpret_cast<float*>(smem + pl.smPlanes);
     const float* wsm = reinterpret_cast<const float*>(smem + pl.smW);
     for (int l = 1; l <= pl.L; ++l) {  // model/recnext.py:27-29
-        ctx.run([&](int tid) {
-            const ThreadPos t = rc_thread_pos(pl, tid, cg);
+        seq.stage(ctx, pl.lv[l].g2.lanes, [&](const ThreadPos& t) {
             if (!t.active) return;
             float* pb = planes + (long)t.p * pl.plane_floats;
             const LevelGeo& gi = pl.lv[l - 1];
@@ -148,8 +162,8 @@ RC_HD void rc_pyramid(Ctx& ctx, const Plan& pl, unsigned char* smem, int cg, boo
             float* dst = pb + go.offS + PAD * go.pitch + PAD;
             float* dstx = (keep_x && go.offX >= 0) ? pb + go.offX + PAD * go.pitch + PAD : nullptr;
             const int pitch = go.pitch, Wo = go.W;
-            rc_conv_s2<K>(pb + gi.offS, gi.pitch, wsm + (t.p * (pl.L + 2) + 0) * pl.wstride, pl.has_bias != 0, go.H, go.W,
-                          go.magic_strips, go.rpi_down, t.lane, pl.g, [&](int row, int c0, const float (&acc)[kStripW]) {
+            rc_conv_s2<K>(pb + gi.offS, gi.pitch, wsm + (t.p * (pl.L + 2) + 0) * pl.wstride, pl.has_bias != 0, go.H, go.g2, t.lane, pl.g,
+                          [&](int row, int c0, const float (&acc)[kStripW]) {
 #pragma unroll
                               for (int c = 0; c < kStripW; ++c)
                                   if (c0 + c < Wo) {
@@ -158,37 +172,30 @@ RC_HD void rc_pyramid(Ctx& ctx, const Plan& pl, unsigned char* smem, int cg, boo
                                   }
                           });
         });
-        ctx.sync();
     }
     for (int l = pl.L; l >= 1; --l) {  // model/recnext.py:31-33 ; convs[L-l] acts on level l
-        ctx.run([&](int tid) {
-            const ThreadPos t = rc_thread_pos(pl, tid, cg);
+        seq.stage(ctx, pl.lv[l].g1.lanes, [&](const ThreadPos& t) {
             if (!t.active) return;
             float* pb = planes + (long)t.p * pl.plane_floats;
             const LevelGeo& gl = pl.lv[l];
             float* T = pb + pl.offT;
             const int Hl = gl.H, Wl = gl.W, tp = gl.tpitch;
             rc_conv_s1<K, false>(pb + gl.offS, gl.pitch, wsm + (t.p * (pl.L + 2) + 1 + (pl.L - l)) * pl.wstride, pl.has_bias != 0,
-                                 gl.H, gl.W, gl.magic_strips, gl.rpi, t.lane, pl.g,
+                                 gl.H, gl.g1, t.lane, pl.g,
                                  [&](int row, int c0, const float (&acc)[kStripW]) { rc_store_T(T, tp, Hl, Wl, row, c0, acc); });
         });
-        ctx.sync();
-        ctx.run([&](int tid) {
-            const ThreadPos t = rc_thread_pos(pl, tid, cg);
+        seq.stage(ctx, pl.lv[l].gu.lanes, [&](const ThreadPos& t) {
             if (!t.active) return;
             float* pb = planes + (long)t.p * pl.plane_floats;
             const LevelGeo& gl = pl.lv[l];
             const LevelGeo& gd = pl.lv[l - 1];
             if (gl.exact2x && pl.mode == 0)
-                rc_upsample2x_add(pb + gd.offS, gd.pitch, PAD, gd.H, gd.W, pb + pl.offT, gl.tpitch, gl.H, gd.magic_strips, gd.nstrips,
-                                  gl.rpu, t.lane, pl.g);
+                rc_upsample2x_add(pb + gd.offS, gd.pitch, PAD, gd.H, gd.W, pb + pl.offT, gl.tpitch, gl.H, gl.gu, t.lane, pl.g);
             else
                 rc_upsample_add(pb + gd.offS, gd.pitch, PAD, gd.H, gd.W, pb + pl.offT, gl.tpitch, gl.H, gl.W,
                                 reinterpret_cast<const IdxLam*>(smem + pl.smTab + gl.tabY),
-                                reinterpret_cast<const IdxLam*>(smem + pl.smTab + gl.tabX), pl.mode, gd.magic_strips, gd.nstrips,
-                                gd.rpi, t.lane, pl.g);
+                                reinterpret_cast<const IdxLam*>(smem + pl.smTab + gl.tabX), pl.mode, gl.gu, t.lane, pl.g);
         });
-        ctx.sync();
     }
 }
 
@@ -229,25 +236,27 @@ RC_HD void rc_forward_body(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsign
         });
     };
     load(first);
+    StageSeq seq{pl.unit_lanes};
     for (int n = first; n < last; ++n) {
         ctx.store_drain();
         ctx.load_wait();
-        rc_unpack_stage<T>(ctx, pl, smem, cg, false, pl.lv[0].offS);
-        ctx.sync();
-        if (n + 1 < last && !pl.share_raw) load(n + 1);
-        rc_pyramid<K>(ctx, pl, smem, cg, false);
-        ctx.run([&](int tid) {  // model/recnext.py:34
-            const ThreadPos t = rc_thread_pos(pl, tid, cg);
+        rc_unpack_stage<T>(ctx, pl, smem, cg, false, pl.lv[0].offS);  // (the previous store synchronised the unit)
+        if (n + 1 < last && !pl.share_raw) {
+            seq.join(ctx, pl.unit_lanes);  // every lane has consumed the raw input
+            load(n + 1);
+        }
+        rc_pyramid<K>(ctx, seq, pl, smem, false);
+        seq.stage(ctx, pl.lv[0].g1.lanes, [&](const ThreadPos& t) {  // model/recnext.py:34
             if (!t.active) return;
             float* pb = planes + (long)t.p * pl.plane_floats;
             const LevelGeo& g0 = pl.lv[0];
             const UnitIO io = rc_unit_io<T>(pl, smem, cg, t.u);
             T* dst = reinterpret_cast<T*>(io.sm_out) + (long)(t.p - t.u * pl.ppu) * HW;
             const int W = pl.W;
-            rc_conv_s1<K, false>(pb + g0.offS, g0.pitch, wsm + (t.p * (pl.L + 2) + 1 + pl.L) * pl.wstride, pl.has_bias != 0, g0.H, g0.W,
-                                 g0.magic_strips, g0.rpi, t.lane, pl.g,
-                                 [&](int row, int c0, const float (&acc)[kStripW]) { rc_store_raw4<T>(dst, W, row, c0, acc); });
+            rc_conv_s1<K, false>(pb + g0.offS, g0.pitch, wsm + (t.p * (pl.L + 2) + 1 + pl.L) * pl.wstride, pl.has_bias != 0, g0.H, g0.g1,
+                                 t.lane, pl.g, [&](int row, int c0, const float (&acc)[kStripW]) { rc_store_raw4<T>(dst, W, row, c0, acc); });
         });
+        seq.prev = pl.unit_lanes;  // ctx.store synchronises the whole unit
         ctx.store([&](int u, void*& dst, const void*& src, long& bytes) {
             const UnitIO io = rc_unit_io<T>(pl, smem, cg, u);
             dst = gy + n * img_stride + io.goff; src = io.sm_out; bytes = io.bytes;
@@ -291,30 +300,29 @@ RC_HD void rc_backward_body(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsig
         });
     };
     if (first < last) load(first);
+    StageSeq seq{pl.unit_lanes};
     for (int n = first; n < last; ++n) {
         ctx.store_drain();
         ctx.load_wait();
-        rc_unpack_stage<T>(ctx, pl, smem, cg, false, g0.offS);
+        rc_unpack_stage<T>(ctx, pl, smem, cg, false, g0.offS);  // (the previous store synchronised the unit)
         rc_unpack_stage<T>(ctx, pl, smem, cg, true, pl.offGY);
-        ctx.sync();
-        rc_pyramid<K>(ctx, pl, smem, cg, true);
+        rc_pyramid<K>(ctx, seq, pl, smem, true);
 
         // y = convs[L](s_0): weight gradient and input gradient
-        ctx.run([&](int tid) {
-            const ThreadPos t = rc_thread_pos(pl, tid, cg);
+        seq.stage(ctx, g0.g1.lanes, [&](const ThreadPos& t) {
             float acc[NA];
 #pragma unroll
             for (int i = 0; i < NA; ++i) acc[i] = 0.f;
             if (t.active) {
                 float* pb = planes + (long)t.p * pl.plane_floats;
-                rc_wgrad_s1<K>(pb + g0.offS, pb + pl.offGY, g0.pitch, g0.H, g0.W, g0.magic_strips, g0.rpi, t.lane, pl.g, acc);
+                rc_wgrad_s1<K>(pb + g0.offS, pb + pl.offGY, g0.pitch, g0.H, g0.g1, t.lane, pl.g, acc);
                 float* G0 = pb + pl.offG0;
                 const UnitIO io = rc_unit_io<T>(pl, smem, cg, t.u);
                 T* dsto = reinterpret_cast<T*>(io.sm_out) + (long)(t.p - t.u * pl.ppu) * HW;
                 const int W = pl.W, gp = pl.pitchG0;
                 const bool direct = (L == 0);
-                rc_conv_s1<K, true>(pb + pl.offGY, g0.pitch, wsm + (t.p * (L + 2) + 1 + L) * pl.wstride, false, g0.H, g0.W,
-                                    g0.magic_strips, g0.rpi, t.lane, pl.g, [&](int row, int c0, const float (&v)[kStripW]) {
+                rc_conv_s1<K, true>(pb + pl.offGY, g0.pitch, wsm + (t.p * (L + 2) + 1 + L) * pl.wstride, false, g0.H, g0.g1, t.lane, pl.g,
+                                    [&](int row, int c0, const float (&v)[kStripW]) {
                                         if (direct) { rc_store_raw4<T>(dsto, W, row, c0, v); return; }
 #pragma unroll
                                         for (int c = 0; c < kStripW; ++c)
@@ -323,13 +331,18 @@ RC_HD void rc_backward_body(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsig
             }
             ctx.template wgrad_commit<NA>(t, pl, acc, slot_of(t, 1 + L));
         });
-        ctx.sync();
 
         for (int l = 1; l <= L; ++l) {
-            // GT_l = up^T(G_{l-1}); S_0 is dead after the stage above, so level 1 also refills it with x_0
-            if (l == 1) rc_unpack_stage<T>(ctx, pl, smem, cg, false, g0.offS);
-            ctx.run([&](int tid) {
-                const ThreadPos t = rc_thread_pos(pl, tid, cg);
+            if (l == 1) {  // S_0 is dead after the stage above: refill it with x_0 for the `down` filter gradient
+                seq.join(ctx, pl.unit_lanes);
+                rc_unpack_stage<T>(ctx, pl, smem, cg, false, g0.offS);
+                if (n + 1 < last && !pl.share_raw) {  // both raw inputs are free from here on: prefetch the next image
+                    seq.join(ctx, pl.unit_lanes);
+                    load(n + 1);
+                }
+            }
+            // GT_l = up^T(G_{l-1})
+            seq.stage(ctx, pl.lv[l].gather_lanes, [&](const ThreadPos& t) {
                 if (!t.active) return;
                 float* pb = planes + (long)t.p * pl.plane_floats;
                 const LevelGeo& gl = pl.lv[l];
@@ -340,21 +353,18 @@ RC_HD void rc_backward_body(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsig
                                 reinterpret_cast<const GatherEntry*>(smem + pl.smTab + gl.gatY),
                                 reinterpret_cast<const GatherEntry*>(smem + pl.smTab + gl.gatX), gl.magic_W, t.lane, pl.g);
             });
-            ctx.sync();
-            if (l == 1 && n + 1 < last && !pl.share_raw) load(n + 1);  // both raw inputs are free from here on
-            ctx.run([&](int tid) {
-                const ThreadPos t = rc_thread_pos(pl, tid, cg);
+            seq.stage(ctx, pl.lv[l].g1.lanes, [&](const ThreadPos& t) {
                 float acc[NA];
 #pragma unroll
                 for (int i = 0; i < NA; ++i) acc[i] = 0.f;
                 if (t.active) {
                     float* pb = planes + (long)t.p * pl.plane_floats;
                     const LevelGeo& gl = pl.lv[l];
-                    rc_wgrad_s1<K>(pb + gl.offS, pb + gl.offGT, gl.pitch, gl.H, gl.W, gl.magic_strips, gl.rpi, t.lane, pl.g, acc);
+                    rc_wgrad_s1<K>(pb + gl.offS, pb + gl.offGT, gl.pitch, gl.H, gl.g1, t.lane, pl.g, acc);
                     float* dst = pb + gl.offGS + PAD * gl.pitch + PAD;
                     const int pitch = gl.pitch, Wl = gl.W;
-                    rc_conv_s1<K, true>(pb + gl.offGT, gl.pitch, wsm + (t.p * (L + 2) + 1 + (L - l)) * pl.wstride, false, gl.H, gl.W,
-                                        gl.magic_strips, gl.rpi, t.lane, pl.g, [&](int row, int c0, const float (&v)[kStripW]) {
+                    rc_conv_s1<K, true>(pb + gl.offGT, gl.pitch, wsm + (t.p * (L + 2) + 1 + (L - l)) * pl.wstride, false, gl.H, gl.g1,
+                                        t.lane, pl.g, [&](int row, int c0, const float (&v)[kStripW]) {
 #pragma unroll
                                             for (int c = 0; c < kStripW; ++c)
                                                 if (c0 + c < Wl) dst[row * pitch + c0 + c] = v[c];
@@ -362,13 +372,12 @@ RC_HD void rc_backward_body(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsig
                 }
                 ctx.template wgrad_commit<NA>(t, pl, acc, slot_of(t, 1 + (L - l)));
             });
-            ctx.sync();
         }
 
         for (int l = L; l >= 1; --l) {
             // x_l = down(x_{l-1}): filter gradient (summed over levels) and input gradient added to G_{l-1}
-            ctx.run([&](int tid) {
-                const ThreadPos t = rc_thread_pos(pl, tid, cg);
+            const int lanes = pl.lv[l].g2.lanes > pl.lv[l].gt.lanes ? pl.lv[l].g2.lanes : pl.lv[l].gt.lanes;
+            seq.stage(ctx, lanes, [&](const ThreadPos& t) {
                 float acc[NA];
 #pragma unroll
                 for (int i = 0; i < NA; ++i) acc[i] = 0.f;
@@ -377,25 +386,25 @@ RC_HD void rc_backward_body(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsig
                     const LevelGeo& gl = pl.lv[l];
                     const LevelGeo& gd = pl.lv[l - 1];
                     const float* X = (l - 1 == 0) ? pb + g0.offS : pb + gd.offX;
-                    rc_wgrad_s2<K>(X, gd.pitch, pb + gl.offGS, gl.pitch, gl.H, gl.W, gl.magic_strips, gl.rpi_down, t.lane, pl.g, acc);
+                    rc_wgrad_s2<K>(X, gd.pitch, pb + gl.offGS, gl.pitch, gl.H, gl.g2, t.lane, pl.g, acc);
                     if (l - 1 == 0) {
                         const float* G0 = pb + pl.offG0;
                         const UnitIO io = rc_unit_io<T>(pl, smem, cg, t.u);
                         T* dsto = reinterpret_cast<T*>(io.sm_out) + (long)(t.p - t.u * pl.ppu) * HW;
                         const int W = pl.W, gp = pl.pitchG0;
-                        rc_convT_s2<K>(pb + gl.offGS, gl.pitch, wsm + (t.p * (L + 2) + 0) * pl.wstride, gd.H, gd.W, t.lane, pl.g,
+                        rc_convT_s2<K>(pb + gl.offGS, gl.pitch, wsm + (t.p * (L + 2) + 0) * pl.wstride, gd.H, gd.W, gl.gt, t.lane, pl.g,
                                        [&](int i, int j, float v) { dsto[i * W + j] = Elem<T>::from_f(G0[i * gp + j] + v); });
                     } else {
                         float* dst = pb + gd.offGS + PAD * gd.pitch + PAD;
                         const int pitch = gd.pitch;
-                        rc_convT_s2<K>(pb + gl.offGS, gl.pitch, wsm + (t.p * (L + 2) + 0) * pl.wstride, gd.H, gd.W, t.lane, pl.g,
+                        rc_convT_s2<K>(pb + gl.offGS, gl.pitch, wsm + (t.p * (L + 2) + 0) * pl.wstride, gd.H, gd.W, gl.gt, t.lane, pl.g,
                                        [&](int i, int j, float v) { dst[i * pitch + j] += v; });
                     }
                 }
                 ctx.template wgrad_commit<NA>(t, pl, acc, slot_of(t, 0));
             });
-            if (l > 1) ctx.sync();
         }
+        seq.prev = pl.unit_lanes;  // ctx.store synchronises the whole unit
         ctx.store([&](int u, void*& dst, const void*& src, long& bytes) {
             const UnitIO io = rc_unit_io<T>(pl, smem, cg, u);
             dst = g_out + n * img_stride + io.goff; src = io.sm_out; bytes = io.bytes;
@@ -409,7 +418,7 @@ RC_HD void rc_backward_body(Ctx& ctx, const Plan& pl, const KernelArgs& a, unsig
 
     // per-CTA partials -> workspace [chunk][(L+2)][C][wstride]; slots of one plane are summed in fixed order
     ctx.cta_sync();
-    ctx.run([&](int tid) {
+    ctx.run_all([&](int tid) {
         const int per_plane = (L + 2) * pl.wstride;
         const int spp = pl.g >= 32 ? pl.g / 32 : 1;  // slots per plane
         for (int i = tid; i < nact * per_plane; i += pl.T) {

@@ -90,13 +90,20 @@ struct DeviceCtx {
     int tid, T, use_tma, g, u, ul, unit_lanes;
     uint32_t bar, phase;
 
-    template <class F> __device__ __forceinline__ void run(F f) { f(tid); }
+    ThreadPos pos;  // computed once per thread
+    template <class F> __device__ __forceinline__ void run_all(F f) { f(tid); }
+    template <class F> __device__ __forceinline__ void run(int n, F f) { if (ul < n) f(pos); }
     __device__ __forceinline__ void cta_sync() { __syncthreads(); }
-    // teams / units never interact: a warp-resident unit needs only __syncwarp, a multi-warp team a named barrier
-    __device__ __forceinline__ void sync() {
-        if (unit_lanes <= 32) __syncwarp();
-        else asm volatile("bar.sync %0, %1;" ::"r"(u + 1), "r"(unit_lanes) : "memory");
+    // Units never interact.  A warp-resident unit needs only __syncwarp; a multi-warp team uses one named barrier
+    // per participant count (64 / 128 / 256 leading lanes), so warps that skip a stage never touch its barrier.
+    __device__ __forceinline__ void sync(int n) {
+        if (unit_lanes <= 32 || n <= 32) { if (ul < 32) __syncwarp(); return; }
+        if (ul < n) {
+            const int id = 1 + u * 3 + (n == 64 ? 0 : (n == 128 ? 1 : 2));
+            asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+        }
     }
+    __device__ __forceinline__ void sync_unit() { sync(unit_lanes); }
 
     template <class F> __device__ __forceinline__ void load_begin(F desc) {
         void *d0, *d1; const void *s0, *s1; long b0, b1;
@@ -118,7 +125,7 @@ struct DeviceCtx {
             while (!rc_mbar_try_wait(bar, phase)) {}
             phase ^= 1u;
         } else {
-            sync();
+            sync_unit();
         }
     }
     template <class F> __device__ __forceinline__ void store(F desc) {
@@ -126,16 +133,16 @@ struct DeviceCtx {
         desc(u, dst, src, bytes);
         if (use_tma) {
             rc_fence_proxy_async();  // make this thread's shared-memory writes visible to the async proxy
-            sync();
+            sync_unit();
             if (ul == 0 && bytes) rc_bulk_s2g(dst, src, (uint32_t)bytes);
         } else {
-            sync();
+            sync_unit();
             rc_coop_copy(dst, src, bytes, ul, unit_lanes);
         }
     }
     __device__ __forceinline__ void store_drain() {
         if (use_tma) { if (ul == 0) rc_bulk_wait_read0(); }
-        else sync();  // cooperative stores of the previous image have finished reading raw out
+        else sync_unit();  // cooperative stores of the previous image have finished reading raw out
     }
 
     // Sum the per-lane partials of one plane (team lanes inside a warp) with a transposed butterfly, then every
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(kMaxThreads, BWD ? 1 : 2) recconv_kernel(const
     if (pl.use_tma && ctx.ul == 0) rc_mbar_init(ctx.bar, 1);
     __syncthreads();
     const int cg = blockIdx.x % pl.n_cg, chunk = blockIdx.x / pl.n_cg;
+    ctx.pos = rc_thread_pos(pl, threadIdx.x, cg);
     if (BWD) rc_backward_body<K, T>(ctx, pl, a, smem, cg, chunk);
     else rc_forward_body<K, T>(ctx, pl, a, smem, cg, chunk);
 }

@@ -32,6 +32,14 @@ constexpr int kMaxLevel = RECNEXT_MAX_LEVEL;
 constexpr int kStripW = 4;  // output columns per work item (one float4 of accumulators)
 constexpr int kMaxThreads = 256;
 
+struct StripGrid {  // work items of one stage: 4-column strips x blocks of `rpi` rows, item = rb * nstrips + strip
+    int nstrips;
+    unsigned magic;  // item / nstrips by multiplication
+    int rpi;         // rows per item
+    int nitems;
+    int lanes;       // leading lanes of the team that take part (power of two >= 32 when the team spans warps)
+};
+
 struct LevelGeo {
     int H, W;        // level size (level 0 = input)
     int pitch;       // floats per padded row
@@ -40,12 +48,13 @@ struct LevelGeo {
     int offX;        // bwd: copy of x_l (levels 1..L-1), -1 if absent
     int offGT;       // bwd: gradient w.r.t. t_l = convs[L-l](s_l) (padded), levels 1..L
     int offGS;       // bwd: gradient w.r.t. s_l, later total gradient of x_l (padded), levels 1..L
-    int rpi;         // rows per work item for stride-1 stencils ON this level
-    int rpi_down;    // rows per work item for the stride-2 stencil PRODUCING this level (l >= 1)
-    int rpu;         // l >= 1: SOURCE rows per work item of the exact-2x upsample into level l-1
+    StripGrid g1;    // stride-1 stencils ON this level (rows of this level)
+    StripGrid g2;    // l >= 1: the stride-2 stencil PRODUCING this level (rows of this level)
+    StripGrid gu;    // l >= 1: upsample of this level INTO level l-1: strips of level l-1; rows are SOURCE rows of
+                     //         this level on the exact-2x path, destination rows of level l-1 on the generic path
+    StripGrid gt;    // l >= 1 (bwd): 2x2 blocks of level l-1 for the transpose of the stride-2 conv (nstrips = blocks per row)
     unsigned magic_W;  // magic for division by W (backward gather)
-    int nstrips;     // ceil(W / 4)
-    unsigned magic_strips;  // floor(2^32 / nstrips) + 1 : item / nstrips == umulhi(item, magic)
+    int gather_lanes;  // bwd: lanes taking part in the gather of this level
     int tpitch;      // l >= 1: pitch of the T buffer of this level ((H+2) x tpitch, replicate border of 1)
     int exact2x;     // l >= 1: level l-1 is exactly 2x this level in both dimensions (bilinear fast path)
     int tabY, tabX;  // byte offsets (table region) of {int i0; float lambda}[H_{l-1}] / [W_{l-1}] (level l-1 -> l)
@@ -141,8 +150,6 @@ RC_H int rc_make_plan(Plan& pl, int B, int C, int H, int W, int K, int L, int mo
     int off = 0;
     for (int l = 0; l <= L; ++l) {
         LevelGeo& g = pl.lv[l];
-        g.nstrips = rc_div_up(g.W, kStripW);
-        g.magic_strips = rc_magic(g.nstrips);
         int need = rc_round_up(g.W, kStripW) - kStripW + rc_win_s1(K);  // stride-1 readers of this level
         if (l < L) {  // the stride-2 stencil producing level l+1 reads this level
             const int n2 = 2 * (rc_round_up(pl.lv[l + 1].W, kStripW) - kStripW) + rc_win_s2(K);
@@ -237,11 +244,37 @@ RC_H int rc_make_plan(Plan& pl, int B, int C, int H, int W, int K, int L, int mo
     pl.share_raw = smem_for(units, false) > opt.smem_limit ? 1 : 0;
     if (smem_for(units, pl.share_raw != 0) > opt.smem_limit) return 1;
 
+    auto lanes_for = [&](int nitems) {
+        if (g <= 32) return 32;  // warp-resident teams: the whole warp takes part in every stage
+        int n = 32;
+        while (n < g && n < nitems) n *= 2;
+        return n;
+    };
+    auto grid = [&](int rows, int cols, int halo) {
+        StripGrid sg;
+        sg.nstrips = rc_div_up(cols, kStripW);
+        sg.magic = rc_magic(sg.nstrips);
+        sg.rpi = rc_pick_rpi(rows, cols, g, halo);
+        sg.nitems = sg.nstrips * rc_div_up(rows, sg.rpi);
+        sg.lanes = lanes_for(sg.nitems);
+        return sg;
+    };
     for (int l = 0; l <= L; ++l) {
-        pl.lv[l].rpi = rc_pick_rpi(pl.lv[l].H, pl.lv[l].W, g, K - 1);
-        pl.lv[l].rpi_down = l >= 1 ? rc_pick_rpi(pl.lv[l].H, pl.lv[l].W, g, K - 2) : 0;
-        pl.lv[l].rpu = l >= 1 ? rc_pick_rpi(pl.lv[l].H, pl.lv[l - 1].W, g, 1) : 0;
-        pl.lv[l].magic_W = rc_magic(pl.lv[l].W);
+        LevelGeo& lg = pl.lv[l];
+        lg.g1 = grid(lg.H, lg.W, K - 1);
+        lg.magic_W = rc_magic(lg.W);
+        lg.gather_lanes = lanes_for(lg.H * lg.W);
+        if (l >= 1) {
+            lg.g2 = grid(lg.H, lg.W, K - 2);
+            const LevelGeo& ld = pl.lv[l - 1];
+            if (lg.exact2x && mode == 0) lg.gu = grid(lg.H, ld.W, 1);
+            else lg.gu = grid(ld.H, ld.W, 0);
+            lg.gt.nstrips = (ld.W + 1) / 2;
+            lg.gt.magic = rc_magic(lg.gt.nstrips);
+            lg.gt.rpi = 1;
+            lg.gt.nitems = lg.gt.nstrips * ((ld.H + 1) / 2);
+            lg.gt.lanes = lanes_for(lg.gt.nitems);
+        }
     }
 
     // shared memory map

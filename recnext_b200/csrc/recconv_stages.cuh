@@ -154,10 +154,10 @@ RC_HD void rc_load_filter(float (&w)[N], const float* __restrict__ wsm, bool fli
 // ---------------------------------------------------------------------------------------------------------
 template <int K, bool FLIP, class Epi>
 RC_HD void rc_conv_s1(const float* __restrict__ src, int pitch, const float* __restrict__ wsm, bool use_bias, int Ho,
-                      int Wo, unsigned magic_strips, int rpi, int lane, int g, Epi epi) {
+                      const StripGrid& sg, int lane, int g, Epi epi) {
     constexpr int WL = (kStripW + 2 * (K / 2) + 3) & ~3;
-    const int nstrips = (Wo + kStripW - 1) / kStripW;
-    const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
+    const int nstrips = sg.nstrips, nitems = sg.nitems, rpi = sg.rpi;
+    const unsigned magic_strips = sg.magic;
     if (lane >= nitems) return;
     float w[K * K];
     rc_load_filter<K * K>(w, wsm, FLIP);
@@ -192,10 +192,10 @@ RC_HD void rc_conv_s1(const float* __restrict__ src, int pitch, const float* __r
 // Stage: depthwise KxK STRIDE-2 cross-correlation (the shared `down` filter): level l-1 (padded) -> level l.
 template <int K, class Epi>
 RC_HD void rc_conv_s2(const float* __restrict__ src, int pitch, const float* __restrict__ wsm, bool use_bias, int Ho,
-                      int Wo, unsigned magic_strips, int rpi, int lane, int g, Epi epi) {
+                      const StripGrid& sg, int lane, int g, Epi epi) {
     constexpr int WL = (2 * (kStripW - 1) + K + 3) & ~3;
-    const int nstrips = (Wo + kStripW - 1) / kStripW;
-    const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
+    const int nstrips = sg.nstrips, nitems = sg.nitems, rpi = sg.rpi;
+    const unsigned magic_strips = sg.magic;
     if (lane >= nitems) return;
     float w[K * K];
     rc_load_filter<K * K>(w, wsm, false);
@@ -275,8 +275,9 @@ RC_HD void rc_hinterp2x(float (&h)[kStripW], const float* __restrict__ trow) {
 }
 
 RC_HD void rc_upsample2x_add(float* __restrict__ dstS, int pitch, int pad, int Hd, int Wd, const float* __restrict__ T, int tp,
-                             int Hl, unsigned magic_strips, int nstrips, int rpu, int lane, int g) {
-    const int nitems = nstrips * ((Hl + rpu - 1) / rpu);
+                             int Hl, const StripGrid& sg, int lane, int g) {
+    const int nstrips = sg.nstrips, nitems = sg.nitems, rpu = sg.rpi;
+    const unsigned magic_strips = sg.magic;
     for (int item = lane; item < nitems; item += g) {
         const int rb = rc_fastdiv(item, magic_strips), q = item - rb * nstrips;
         const int m_begin = rb * rpu;
@@ -317,8 +318,9 @@ RC_HD void rc_upsample2x_add(float* __restrict__ dstS, int pitch, int pad, int H
 // Generic path (odd sizes such as 7 -> 4, nearest mode): table driven.  Items = 4 columns x rpi rows of level l-1.
 RC_HD void rc_upsample_add(float* __restrict__ dstS, int pitch, int pad, int Hd, int Wd, const float* __restrict__ T, int tp,
                            int Hl, int Wl, const IdxLam* __restrict__ ytab, const IdxLam* __restrict__ xtab, int mode,
-                           unsigned magic_strips, int nstrips, int rpi, int lane, int g) {
-    const int nitems = nstrips * ((Hd + rpi - 1) / rpi);
+                           const StripGrid& sg, int lane, int g) {
+    const int nstrips = sg.nstrips, nitems = sg.nitems, rpi = sg.rpi;
+    const unsigned magic_strips = sg.magic;
     for (int item = lane; item < nitems; item += g) {
         const int rb = rc_fastdiv(item, magic_strips), q = item - rb * nstrips;
         const int j0 = q * kStripW;
@@ -385,12 +387,12 @@ RC_HD void rc_upsample_bwd(float* __restrict__ dstGT, int pitch, int pad, int Hl
 // lane's items; acc[K*K] += sum G (bias gradient).  S and G are padded buffers of the same level geometry.
 // ---------------------------------------------------------------------------------------------------------
 template <int K>
-RC_HD void rc_wgrad_s1(const float* __restrict__ S, const float* __restrict__ G, int pitch, int Ho, int Wo,
-                       unsigned magic_strips, int rpi, int lane, int g, float (&acc)[K * K + 1]) {
+RC_HD void rc_wgrad_s1(const float* __restrict__ S, const float* __restrict__ G, int pitch, int Ho, const StripGrid& sg,
+                       int lane, int g, float (&acc)[K * K + 1]) {
     constexpr int WL = (kStripW + 2 * (K / 2) + 3) & ~3;
     constexpr int PAD = K / 2;
-    const int nstrips = (Wo + kStripW - 1) / kStripW;
-    const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
+    const int nstrips = sg.nstrips, nitems = sg.nitems, rpi = sg.rpi;
+    const unsigned magic_strips = sg.magic;
     for (int item = lane; item < nitems; item += g) {
         const int rb = rc_fastdiv(item, magic_strips), st = item - rb * nstrips;
         const int r0 = rb * rpi, c0 = st * kStripW;
@@ -424,12 +426,12 @@ RC_HD void rc_wgrad_s1(const float* __restrict__ S, const float* __restrict__ G,
 
 // Weight gradient of the stride-2 `down` conv: X = padded level l-1 input, G = padded total gradient of x_l.
 template <int K>
-RC_HD void rc_wgrad_s2(const float* __restrict__ X, int xpitch, const float* __restrict__ G, int gpitch, int Ho, int Wo,
-                       unsigned magic_strips, int rpi, int lane, int g, float (&acc)[K * K + 1]) {
+RC_HD void rc_wgrad_s2(const float* __restrict__ X, int xpitch, const float* __restrict__ G, int gpitch, int Ho,
+                       const StripGrid& sg, int lane, int g, float (&acc)[K * K + 1]) {
     constexpr int WL = (2 * (kStripW - 1) + K + 3) & ~3;
     constexpr int PAD = K / 2;
-    const int nstrips = (Wo + kStripW - 1) / kStripW;
-    const int nitems = nstrips * ((Ho + rpi - 1) / rpi);
+    const int nstrips = sg.nstrips, nitems = sg.nitems, rpi = sg.rpi;
+    const unsigned magic_strips = sg.magic;
     for (int item = lane; item < nitems; item += g) {
         const int rb = rc_fastdiv(item, magic_strips), st = item - rb * nstrips;
         const int r0 = rb * rpi, c0 = st * kStripW;
@@ -469,18 +471,17 @@ RC_HD void rc_wgrad_s2(const float* __restrict__ X, int xpitch, const float* __r
 // G is the padded total gradient of x_l; outputs cover level l-1 (Ho x Wo).  epi(i, j, value_without_base).
 // ---------------------------------------------------------------------------------------------------------
 template <int K, class Epi>
-RC_HD void rc_convT_s2(const float* __restrict__ G, int gpitch, const float* __restrict__ wsm, int Ho, int Wo, int lane,
-                       int g, Epi epi) {
+RC_HD void rc_convT_s2(const float* __restrict__ G, int gpitch, const float* __restrict__ wsm, int Ho, int Wo,
+                       const StripGrid& sg, int lane, int g, Epi epi) {
     constexpr int PAD = K / 2;
     constexpr int LO = -(PAD / 2);
     constexpr int NW = PAD + 1;
-    const int na = (Ho + 1) >> 1, nb = (Wo + 1) >> 1;
-    const int nitems = na * nb;
+    const int nb = sg.nstrips, nitems = sg.nitems;
     if (lane >= nitems) return;
     float w[K * K];
     rc_load_filter<K * K>(w, wsm, false);
     for (int item = lane; item < nitems; item += g) {
-        const int a = item / nb, b = item - a * nb;
+        const int a = rc_fastdiv(item, sg.magic), b = item - a * nb;
         float gw[NW][NW];
         const float* gp = G + (a + LO + PAD) * gpitch + (b + LO + PAD);
 #pragma unroll

@@ -18,9 +18,16 @@
 using namespace recnext;
 
 struct HostCtx {
-    int T, n_units;
-    template <class F> __host__ __device__ void run(F f) { for (int t = 0; t < T; ++t) f(t); }
-    __host__ __device__ void sync() {}
+    int T, n_units, cg;
+    const Plan* pl;
+    template <class F> __host__ __device__ void run_all(F f) { for (int t = 0; t < T; ++t) f(t); }
+    template <class F> __host__ __device__ void run(int n, F f) {
+        for (int t = 0; t < T; ++t) {
+            const ThreadPos pos = rc_thread_pos(*pl, t, cg);
+            if (pos.ul < n) f(pos);
+        }
+    }
+    __host__ __device__ void sync(int) {}
     __host__ __device__ void cta_sync() {}
     template <class F> __host__ __device__ void load_begin(F desc) {
         for (int u = 0; u < n_units; ++u) {
@@ -51,8 +58,8 @@ static void run_all(const Plan& pl, const KernelArgs& a, bool bwd) {
     for (int blk = 0; blk < pl.n_cg * pl.n_chunk; ++blk) {
         // poison shared memory so that reads of never-written (non-zeroed) cells show up as NaN
         memset(smem, 0xff, pl.smem_bytes);
-        HostCtx ctx{pl.T, pl.n_units};
         const int cg = blk % pl.n_cg, chunk = blk / pl.n_cg;
+        HostCtx ctx{pl.T, pl.n_units, cg, &pl};
         if (bwd) rc_backward_body<K, T>(ctx, pl, a, smem, cg, chunk);
         else rc_forward_body<K, T>(ctx, pl, a, smem, cg, chunk);
     }
