@@ -8,8 +8,22 @@
 
 #include "../../include/recnext_b200.h"
 #include "recconv_body.cuh"
+#include "wplan.h"
+#include <stdlib.h>
 
 namespace recnext {
+template <int K, typename T, bool BWD> cudaError_t w_launch(const WPlan&, const KernelArgs&, cudaStream_t);
+typedef cudaError_t (*w_launch_fn)(const WPlan&, const KernelArgs&, cudaStream_t);
+#define W_DECLARE_K(K)                                                                                           \
+    extern template cudaError_t w_launch<K, float, false>(const WPlan&, const KernelArgs&, cudaStream_t);          \
+    extern template cudaError_t w_launch<K, __nv_bfloat16, false>(const WPlan&, const KernelArgs&, cudaStream_t);  \
+    extern template cudaError_t w_launch<K, __half, false>(const WPlan&, const KernelArgs&, cudaStream_t);         \
+    extern template cudaError_t w_launch<K, float, true>(const WPlan&, const KernelArgs&, cudaStream_t);           \
+    extern template cudaError_t w_launch<K, __nv_bfloat16, true>(const WPlan&, const KernelArgs&, cudaStream_t);   \
+    extern template cudaError_t w_launch<K, __half, true>(const WPlan&, const KernelArgs&, cudaStream_t);
+W_DECLARE_K(3)
+W_DECLARE_K(5)
+W_DECLARE_K(7)
 typedef cudaError_t (*rc_launch_fn)(const Plan&, const KernelArgs&, cudaStream_t);
 template <int K, typename T, bool BWD> cudaError_t rc_launch(const Plan&, const KernelArgs&, cudaStream_t);
 
@@ -51,6 +65,30 @@ static rc_launch_fn pick(int k, int dtype, bool bwd) {
     return nullptr;
 }
 
+template <int K>
+static w_launch_fn w_pick_dtype(int dtype, bool bwd) {
+    switch (dtype) {
+        case RECNEXT_F32: return bwd ? w_launch<K, float, true> : w_launch<K, float, false>;
+        case RECNEXT_BF16: return bwd ? w_launch<K, __nv_bfloat16, true> : w_launch<K, __nv_bfloat16, false>;
+        case RECNEXT_F16: return bwd ? w_launch<K, __half, true> : w_launch<K, __half, false>;
+    }
+    return nullptr;
+}
+static w_launch_fn w_pick(int k, int dtype, bool bwd) {
+    switch (k) {
+        case 3: return w_pick_dtype<3>(dtype, bwd);
+        case 5: return w_pick_dtype<5>(dtype, bwd);
+        case 7: return w_pick_dtype<7>(dtype, bwd);
+    }
+    return nullptr;
+}
+// RECNEXT_PATH=legacy forces the big-plane kernels (A/B measurements); default: team-resident path when it fits
+static bool legacy_forced() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RECNEXT_PATH"); v = (e && strcmp(e, "legacy") == 0) ? 1 : 0; }
+    return v == 1;
+}
+
 static int device_sms() {
     static int sms = 0;
     if (sms == 0) {
@@ -83,6 +121,19 @@ static int make_plan(const recconv_desc* d, bool bwd, Plan& pl) {
                     d->H, d->W, d->level, bwd ? "backward" : "forward");
     if (rc) return fail(RECNEXT_EINVAL, "recconv: bad arguments");
     return 0;
+}
+
+// 0: team-resident plan made; 1: not eligible (use the big-plane path)
+static int make_wplan(const recconv_desc* d, bool bwd, WPlan& pl) {
+    if (legacy_forced() || !w_pick(d->k, d->dtype, bwd)) return 1;
+    WPlanOptions opt;
+    opt.num_sms = device_sms();
+    // tuning overrides for experiments (tools/kbench.py): RECNEXT_G / RECNEXT_TW / RECNEXT_NT / RECNEXT_MAXW
+    if (const char* e = getenv("RECNEXT_G")) opt.force_G = atoi(e);
+    if (const char* e = getenv("RECNEXT_TW")) opt.force_TW = atoi(e);
+    if (const char* e = getenv("RECNEXT_NT")) opt.force_NT = atoi(e);
+    if (const char* e = getenv("RECNEXT_MAXW")) opt.max_warps = atoi(e);
+    return w_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, bwd ? 1 : 0, opt) == 0 ? 0 : 1;
 }
 
 static int fill_args(const recconv_desc* d, const recconv_params* p, KernelArgs& a) {
@@ -128,9 +179,16 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
     if (!x || !y) return fail(RECNEXT_EINVAL, "recconv_forward: null tensor");
     KernelArgs a;
     if (int rc = fill_args(d, p, a)) return rc;
+    a.x = x; a.out = y;
+    WPlan wp;
+    if (make_wplan(d, false, wp) == 0) {
+        if (((uintptr_t)x & 15) != 0) wp.use_tma = 0;  // bulk copies need 16-byte aligned sources
+        const cudaError_t e = w_pick(d->k, d->dtype, false)(wp, a, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward: %s", cudaGetErrorString(e));
+        return RECNEXT_OK;
+    }
     Plan pl;
     if (int rc = make_plan(d, false, pl)) return rc;
-    a.x = x; a.out = y;
     rc_launch_fn fn = pick(d->k, d->dtype, false);
     const cudaError_t e = fn(pl, a, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward: %s", cudaGetErrorString(e));
@@ -140,6 +198,8 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
 RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
     if (check_desc(d)) return 0;
     if (d->B == 0 || d->C == 0) return 0;
+    WPlan wp;
+    if (make_wplan(d, true, wp) == 0) return (size_t)wp.ws_partial_floats * sizeof(float);
     Plan pl;
     if (make_plan(d, true, pl)) return 0;
     return (size_t)pl.ws_partial_floats * sizeof(float);
@@ -161,19 +221,32 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
     if (!x || !gy || !gx) return fail(RECNEXT_EINVAL, "recconv_backward: null tensor");
     KernelArgs a;
     if (int rc = fill_args(d, p, a)) return rc;
-    Plan pl;
-    if (int rc = make_plan(d, true, pl)) return rc;
-    const size_t need = (size_t)pl.ws_partial_floats * sizeof(float);
-    if (!workspace || workspace_bytes < need)
-        return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
     a.x = x; a.gy = gy; a.out = gx; a.partial = reinterpret_cast<float*>(workspace);
-    rc_launch_fn fn = pick(d->k, d->dtype, true);
-    cudaError_t e = fn(pl, a, (cudaStream_t)stream);
+    WPlan wp;
+    Plan pl;
+    int n_partials = 0, wstride = 0;
+    cudaError_t e;
+    if (make_wplan(d, true, wp) == 0) {
+        const size_t need = (size_t)wp.ws_partial_floats * sizeof(float);
+        if (!workspace || workspace_bytes < need)
+            return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
+        if ((((uintptr_t)x | (uintptr_t)gy) & 15) != 0) wp.use_tma = 0;
+        e = w_pick(d->k, d->dtype, true)(wp, a, (cudaStream_t)stream);
+        n_partials = wp.tpc; wstride = wp.wstride;
+    } else {
+        if (int rc = make_plan(d, true, pl)) return rc;
+        const size_t need = (size_t)pl.ws_partial_floats * sizeof(float);
+        if (!workspace || workspace_bytes < need)
+            return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
+        rc_launch_fn fn = pick(d->k, d->dtype, true);
+        e = fn(pl, a, (cudaStream_t)stream);
+        n_partials = pl.n_chunk; wstride = pl.wstride;
+    }
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward: %s", cudaGetErrorString(e));
-    const long total = (long)(d->level + 2) * d->C * pl.wstride;
+    const long total = (long)(d->level + 2) * d->C * wstride;
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads);
-    recconv_wgrad_finalize<<<blocks, threads, 0, (cudaStream_t)stream>>>(a.partial, gw, gb, pl.n_chunk, d->level + 2, d->C, KK, pl.wstride);
+    recconv_wgrad_finalize<<<blocks, threads, 0, (cudaStream_t)stream>>>(a.partial, gw, gb, n_partials, d->level + 2, d->C, KK, wstride);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward(finalize): %s", cudaGetErrorString(e));
     return RECNEXT_OK;
@@ -182,6 +255,15 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen) {
     if (int rc = check_desc(d)) return rc;
     if (!buf || !buflen) return fail(RECNEXT_EINVAL, "recconv_plan_describe: null buffer");
+    WPlan wp;
+    if (make_wplan(d, backward != 0, wp) == 0) {
+        snprintf(buf, buflen,
+                 "%s team-resident k=%d L=%d [%d,%d,%d,%d] planes/batch=%d warps/team=%d teams/CTA=%d threads=%d grid=%d lanes/plane=%d "
+                 "teams/channel-group=%d smem=%d B team=%d B plane=%d B tma=%d",
+                 backward ? "bwd" : "fwd", wp.K, wp.L, wp.B, wp.C, wp.H, wp.W, wp.G, wp.TW, wp.NT, wp.threads, wp.grid, wp.LPP, wp.tpc,
+                 wp.smem_bytes, wp.team_bytes, wp.plane_floats * 4, wp.use_tma);
+        return RECNEXT_OK;
+    }
     Plan pl;
     if (int rc = make_plan(d, backward != 0, pl)) return rc;
     int n = snprintf(buf, buflen,

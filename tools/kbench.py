@@ -35,6 +35,7 @@ def timeit(fn, flush, iters=10, warm=3):
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
+        torch.cuda._sleep(400000)  # keeps the GPU busy while the host enqueues: events then bracket device time only
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record()
