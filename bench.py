@@ -139,6 +139,7 @@ def recconv_microbench(torch, R, peak):
         gy = torch.randn(shape, device="cuda").bfloat16()
         tf, tb = [], []
         for i in range(6):
+            torch.cuda._sleep(400000)  # the GPU stays busy while the host enqueues: events bracket device time only
             flush.zero_()
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record(); R.recconv_forward(x, ws, None, 5, L, "bilinear")
@@ -164,6 +165,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--memory-format", default="contiguous", choices=["contiguous", "channels_last"],
+                    help="memory format of the model around RecConv2d (the RecConv kernels always work on NCHW planes)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,9 +178,9 @@ def main():
         args.warmup = 3
 
     import torch
-    import torch.distributed as dist
 
     import recnext_b200 as R
+    from recnext_b200 import dist as D
     from recnext_b200 import recconv as RC
     from recnext_b200.model import create_model, replace_batchnorm
 
@@ -185,16 +188,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the RecConv path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    D.init("nccl", dev)
     torch.backends.cudnn.benchmark = True  # as the reference harness does (main.py:213)
 
     torch.manual_seed(0 + rank)
     net = create_model(MODEL).eval()
     replace_batchnorm(net)  # the "fused-BN eval model" (speed_gpu.py:48)
     net.to(dev)
+    cl = args.memory_format == "channels_last"
+    if cl:
+        net.to(memory_format=torch.channels_last)
     x_dev = torch.randn(BATCH, 3, RES, RES, device=dev).bfloat16()
+    if cl:
+        x_dev = x_dev.contiguous(memory_format=torch.channels_last)
     x_host = torch.randn(BATCH, 3, RES, RES).bfloat16().pin_memory()
     y_host = torch.empty(BATCH, 1000, dtype=torch.bfloat16).pin_memory()
     x_stage = torch.empty_like(x_dev)
@@ -206,13 +212,11 @@ def main():
     def step_e2e():
         x_stage.copy_(x_host, non_blocking=True)
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            y = net(x_stage)
+            y = net(x_stage.contiguous(memory_format=torch.channels_last) if cl else x_stage)
         y_host.copy_(y, non_blocking=True)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        D.barrier(dev)
 
     def timed(fn, steps, instrument=False):
         barrier()
@@ -226,10 +230,7 @@ def main():
         barrier()
         ms = a.elapsed_time(b)
         launches = RC.timing_end() if instrument else None
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = D.max_over_ranks(ms, dev)
         return ms, launches
 
     for _ in range(args.warmup):
@@ -243,8 +244,8 @@ def main():
     ms_e2e, _ = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
-    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+    value = D.job_throughput(BATCH, world, args.steps, ms_total)
+    e2e_value = D.job_throughput(BATCH, world, args.steps, ms_e2e)
 
     # roofline of the dominant kernel of the step (the fused RecConv forward kernel, 21 launches per step)
     peak, peak_src = hbm_peak()
@@ -255,19 +256,20 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get("recconv_fwd_bytes_per_launch")
+            traffic = json.load(fh).get("recconv_fwd_dram_bytes_per_launch_avg")
     except Exception:
         pass
     roofline = {
-        "bound": "hbm", "kernel": "recnext::recconv_kernel<5,bf16,fwd> (all RecConv2d launches of the step)",
+        "bound": "hbm", "kernel": "recnext::recconv_wfwd_kernel<5,bf16> (team-resident fused RecConv forward; all 21 launches of a step)",
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
         "peak_source": peak_src, "bytes_per_launch": alg_bytes / max(n_launch, 1), "avg_launch_ms": kern_ms / max(n_launch, 1),
         "share_of_step": round(kern_ms / ms_total, 4),
+        "note": "algorithmic bytes 2*N*e per launch (SURVEY 8d); the kernel is FP32-FMA-pipe bound, not HBM bound: "
+                "ceiling ~33% of HBM peak in bf16 (DESIGN.md 3.2)",
     }
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        D.finalize()
         return
 
     out = {
@@ -276,6 +278,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "model": MODEL, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "resolution": RES,
                    "parallelism": f"replicas x{world} (no data-path collective)", "weights": "random-init",
+                   "memory_format": args.memory_format + " around RecConv2d (cuDNN 1x1 convs); RecConv2d itself on NCHW planes",
                    "l2": "per-step activations (>= 100 MB per stage-0 tensor) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": x_host.numel() * 2,
@@ -290,8 +293,7 @@ def main():
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"16 images/step x 3 steps of the same model (fp32, eval, BN folded, PyTorch CPU eager, {threads} threads)"}
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.finalize()
 
 
 if __name__ == "__main__":

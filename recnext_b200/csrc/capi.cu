@@ -89,6 +89,20 @@ static bool legacy_forced() {
     return v == 1;
 }
 
+// RECNEXT_PROF=1: team 0 of CTA 0 records clock64() after every stage into a 32 KB device buffer that
+// recnext_debug_prof() copies out (timing experiments only; not part of the documented ABI)
+static long long* g_prof = nullptr;
+static long long* prof_buffer() {
+    static int init = 0;
+    if (!init) {
+        init = 1;
+        const char* e = getenv("RECNEXT_PROF");
+        if (e && atoi(e)) { if (cudaMalloc(&g_prof, 4096 * sizeof(long long)) != cudaSuccess) g_prof = nullptr; }
+    }
+    if (g_prof) cudaMemset(g_prof, 0, 4096 * sizeof(long long));
+    return g_prof;
+}
+
 static int device_sms() {
     static int sms = 0;
     if (sms == 0) {
@@ -133,6 +147,7 @@ static int make_wplan(const recconv_desc* d, bool bwd, WPlan& pl) {
     if (const char* e = getenv("RECNEXT_TW")) opt.force_TW = atoi(e);
     if (const char* e = getenv("RECNEXT_NT")) opt.force_NT = atoi(e);
     if (const char* e = getenv("RECNEXT_MAXW")) opt.max_warps = atoi(e);
+    if (const char* e = getenv("RECNEXT_DBG")) opt.dbg = atoi(e);
     return w_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, bwd ? 1 : 0, opt) == 0 ? 0 : 1;
 }
 
@@ -182,6 +197,7 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
     a.x = x; a.out = y;
     WPlan wp;
     if (make_wplan(d, false, wp) == 0) {
+        a.prof = prof_buffer();
         if (((uintptr_t)x & 15) != 0) wp.use_tma = 0;  // bulk copies need 16-byte aligned sources
         const cudaError_t e = w_pick(d->k, d->dtype, false)(wp, a, (cudaStream_t)stream);
         if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward: %s", cudaGetErrorString(e));
@@ -231,6 +247,7 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
         if (!workspace || workspace_bytes < need)
             return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
         if ((((uintptr_t)x | (uintptr_t)gy) & 15) != 0) wp.use_tma = 0;
+        a.prof = prof_buffer();
         e = w_pick(d->k, d->dtype, true)(wp, a, (cudaStream_t)stream);
         n_partials = wp.tpc; wstride = wp.wstride;
     } else {
@@ -250,6 +267,12 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward(finalize): %s", cudaGetErrorString(e));
     return RECNEXT_OK;
+}
+
+RECNEXT_API int recnext_debug_prof(long long* host_out, int n) {
+    if (!g_prof) return 0;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, g_prof, sizeof(long long) * (n < 4096 ? n : 4096), cudaMemcpyDeviceToHost) == cudaSuccess ? 1 : 0;
 }
 
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen) {

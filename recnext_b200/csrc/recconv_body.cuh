@@ -28,6 +28,7 @@ struct KernelArgs {
     float* partial;   // bwd: [n_chunk][(L+2)][C][wstride]
     const void* w[kMaxLevel + 2];  // slot 0 = down, 1+j = convs[j]
     const void* b[kMaxLevel + 2];  // may be null
+    long long* prof;  // timing experiments only (RECNEXT_PROF): per-stage clock64() of team 0 of CTA 0, else null
 };
 
 struct ThreadPos {

@@ -104,6 +104,7 @@ RC_HD void w_pyramid(Ctx& ctx, const WPlan& pl, unsigned char* smem, unsigned ch
     const int LPP = pl.LPP;
     const bool use_bias = pl.has_bias != 0;
     for (int l = 1; l <= pl.L; ++l) {  // model/recnext.py:27-29
+        if (pl.dbg & 2) break;
         ctx.stage([&](int tl) {
             const WLanePos p = w_lane_pos(pl, tsm, tl);
             const WLevel& gi = pl.lv[l - 1];
@@ -119,22 +120,26 @@ RC_HD void w_pyramid(Ctx& ctx, const WPlan& pl, unsigned char* smem, unsigned ch
         });
     }
     for (int l = pl.L; l >= 1; --l) {  // model/recnext.py:31-33 ; convs[L-l] acts on level l
-        ctx.stage([&](int tl) {
+        if (!(pl.dbg & 4)) ctx.stage([&](int tl) {
             const WLanePos p = w_lane_pos(pl, tsm, tl);
             const WLevel& gl = pl.lv[l];
             float* T = p.Tg;
-            const int tp = gl.tp;
+            const int tp = gl.tp, Wl = gl.W;
+            const bool fast = gl.up_fast != 0;
             w_conv_s1<K, false>(p.pb + gl.offS, gl.pitch, gl.H, gl.g1, p.wp + (1 + (pl.L - l)) * pl.wstride, use_bias, p.jl, LPP,
                                 [&](int row, int c0, const float (&acc)[kStripW]) {
-                                    *reinterpret_cast<float4*>(T + row * tp + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                                    if (fast) w_store_T_fast(T, tp, Wl, row, c0, acc);
+                                    else *reinterpret_cast<float4*>(T + row * tp + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                                 });
         });
-        ctx.stage([&](int tl) {
+        if (!(pl.dbg & 8)) ctx.stage([&](int tl) {
             const WLanePos p = w_lane_pos(pl, tsm, tl);
             const WLevel& gl = pl.lv[l];
             const WLevel& gd = pl.lv[l - 1];
             float* dstS = p.pb + gd.offS + PAD * gd.pitch + PAD;
-            if (gl.exact2x && pl.mode == 0)
+            if (gl.up_fast)
+                w_up2x_add_fast(p.pb + gd.offS + PAD * gd.pitch, gd.pitch, PAD, gd.W, p.Tg, gl.tp, gl.H, gl.gu, p.jl, LPP);
+            else if (gl.exact2x && pl.mode == 0)
                 w_up2x_add(dstS, gd.pitch, gd.W, p.Tg, gl.tp, gl.H, gl.W, gl.gu, p.jl, LPP);
             else
                 w_up_add(dstS, gd.pitch, gd.H, gd.W, p.Tg, gl.tp, gl.H, gl.W, reinterpret_cast<const IdxLam*>(smem + pl.smTab + gl.tabY),
@@ -145,6 +150,15 @@ RC_HD void w_pyramid(Ctx& ctx, const WPlan& pl, unsigned char* smem, unsigned ch
 
 template <typename T, class Ctx>
 RC_HD void w_unpack(Ctx& ctx, const WPlan& pl, unsigned char* tsm, const void* raw, int off_dst) {
+    if (pl.dbg & 1) return;
+    if ((pl.W & 1) == 0 && (pl.K / 2) % 2 == 0) {  // column pairs: conflict-free 32/64-bit loads and 64-bit stores
+        ctx.stage([&](int tl) {
+            const WLanePos p = w_lane_pos(pl, tsm, tl);
+            w_unpack_pairs<T>(reinterpret_cast<const T*>(raw) + (long)p.g * pl.H * pl.W, pl.H, pl.W,
+                              p.pb + off_dst + (pl.K / 2) * pl.lv[0].pitch + pl.K / 2, pl.lv[0].pitch, pl.gp, p.jl, pl.LPP);
+        });
+        return;
+    }
     ctx.stage([&](int tl) {
         rc_unpack_unit<T>(reinterpret_cast<const T*>(raw), pl.G, pl.H, pl.W, pl.vec, pl.magic_cpr, pl.magic_H,
                           reinterpret_cast<float*>(tsm + pl.off_planes), pl.plane_floats, off_dst, pl.lv[0].pitch, pl.K / 2, tl,
@@ -179,7 +193,7 @@ RC_HD void w_forward_team(Ctx& ctx, const WPlan& pl, const KernelArgs& a, unsign
         if (pl.L == 0 && nxt.valid()) ctx.load(raw, src_of(nxt), pl.raw_bytes, 0);
         w_pyramid<K>(ctx, pl, smem, tsm, false);
         if (pl.L > 0 && nxt.valid()) ctx.load(raw, src_of(nxt), pl.raw_bytes, 0);  // T is dead: prefetch under the last conv
-        ctx.stage([&](int tl) {  // model/recnext.py:34
+        if (!(pl.dbg & 16)) ctx.stage([&](int tl) {  // model/recnext.py:34
             const WLanePos p = w_lane_pos(pl, tsm, tl);
             const WLevel& g0 = pl.lv[0];
             T* dst = gy + ((long)cur.n * pl.C + (long)cur.cg * pl.G + p.g) * plane_elems;
@@ -262,7 +276,7 @@ RC_HD void w_backward_team(Ctx& ctx, const WPlan& pl, const KernelArgs& a, unsig
         if (nxt.valid()) ctx.load(raw2, gg_in + off_of(nxt), pl.raw_bytes, 1);
 
         // y = convs[L](s_0): filter gradient, then (S_0 is dead) the input gradient G_0 written over it
-        ctx.stage([&](int tl) {
+        if (!(pl.dbg & 32)) ctx.stage([&](int tl) {
             const WLanePos p = w_lane_pos(pl, tsm, tl);
             float acc[NA];
 #pragma unroll
@@ -270,7 +284,7 @@ RC_HD void w_backward_team(Ctx& ctx, const WPlan& pl, const KernelArgs& a, unsig
             w_wgrad_s1<K>(p.pb + g0.offS, p.pb + pl.offGY, g0.pitch, g0.H, g0.g1, p.jl, LPP, acc);
             ctx.template reduce<NA>(pl, tl, acc, slot_of(p, 1 + L));
         });
-        ctx.stage([&](int tl) {
+        if (!(pl.dbg & 64)) ctx.stage([&](int tl) {
             const WLanePos p = w_lane_pos(pl, tsm, tl);
             float* G0 = p.pb + pl.offG0;
             T* dsto = g_out + off_of(cur) + (long)p.g * plane_elems;
@@ -289,7 +303,7 @@ RC_HD void w_backward_team(Ctx& ctx, const WPlan& pl, const KernelArgs& a, unsig
         }
 
         for (int l = 1; l <= L; ++l) {
-            ctx.stage([&](int tl) {  // GT_l = up^T(G_{l-1})
+            if (!(pl.dbg & 128)) ctx.stage([&](int tl) {  // GT_l = up^T(G_{l-1})
                 const WLanePos p = w_lane_pos(pl, tsm, tl);
                 const WLevel& gl = pl.lv[l];
                 const WLevel& gd = pl.lv[l - 1];
@@ -299,7 +313,7 @@ RC_HD void w_backward_team(Ctx& ctx, const WPlan& pl, const KernelArgs& a, unsig
                          reinterpret_cast<const GatherEntry*>(smem + pl.smTab + gl.gatY),
                          reinterpret_cast<const GatherEntry*>(smem + pl.smTab + gl.gatX), gl.magic_W, p.jl, LPP);
             });
-            ctx.stage([&](int tl) {  // dconvs[L-l] = corr(S_l, GT_l);  G_l = convs[L-l]^T GT_l
+            if (!(pl.dbg & 256)) ctx.stage([&](int tl) {  // dconvs[L-l] = corr(S_l, GT_l);  G_l = convs[L-l]^T GT_l
                 const WLanePos p = w_lane_pos(pl, tsm, tl);
                 const WLevel& gl = pl.lv[l];
                 float acc[NA];
@@ -314,7 +328,7 @@ RC_HD void w_backward_team(Ctx& ctx, const WPlan& pl, const KernelArgs& a, unsig
             });
         }
         for (int l = L; l >= 1; --l) {  // x_l = down(x_{l-1}): filter gradient (summed over levels), input gradient into G_{l-1}
-            ctx.stage([&](int tl) {
+            if (!(pl.dbg & 512)) ctx.stage([&](int tl) {
                 const WLanePos p = w_lane_pos(pl, tsm, tl);
                 const WLevel& gl = pl.lv[l];
                 const WLevel& gd = pl.lv[l - 1];

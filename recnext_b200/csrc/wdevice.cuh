@@ -15,9 +15,12 @@ struct WDeviceCtx {
         if (team_lanes == 32) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(team_lanes) : "memory");
     }
+    long long* prof;
+    int prof_i;
     template <class F> __device__ __forceinline__ void stage(F f) {
         f(tl);
         team_sync();
+        if (prof && tl == 0 && prof_i < 4000) prof[prof_i++] = clock64();
     }
     // The team has passed a barrier since its last access to dst.  With TMA, lane 0 issues one bulk copy that
     // completes on the team's mbarrier of queue q; otherwise the lanes copy cooperatively (unaligned batches).
@@ -86,6 +89,7 @@ __device__ __forceinline__ void w_kernel_prologue(WDeviceCtx& ctx, const WPlan& 
     ctx.tl = threadIdx.x - ctx.team * pl.team_lanes;
     ctx.use_tma = pl.use_tma;
     ctx.LPP = pl.LPP;
+    ctx.prof = nullptr; ctx.prof_i = 0;
     for (int q = 0; q < 2; ++q) {
         ctx.bar[q] = rc_smem_u32(smem + pl.smBar + 16 * ctx.team + 8 * q);
         ctx.phase[q] = 0; ctx.pending[q] = false;
@@ -102,16 +106,18 @@ __global__ void __launch_bounds__(MAXT, 1) recconv_wfwd_kernel(const __grid_cons
     extern __shared__ __align__(128) unsigned char smem[];
     WDeviceCtx ctx;
     w_kernel_prologue<K, T, MAXT>(ctx, pl, smem);
+    if (a.prof && blockIdx.x == 0 && ctx.team == 0) { ctx.prof = a.prof; if (ctx.tl == 0) ctx.prof[ctx.prof_i++] = clock64(); }
     w_forward_team<K, T>(ctx, pl, a, smem, ctx.team, blockIdx.x * pl.NT + ctx.team);
 }
 
-template <int K, typename T>
-__global__ void __launch_bounds__(256, 1) recconv_wbwd_kernel(const __grid_constant__ WPlan pl, const __grid_constant__ KernelArgs a) {
+template <int K, typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) recconv_wbwd_kernel(const __grid_constant__ WPlan pl, const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     WDeviceCtx ctx;
-    w_kernel_prologue<K, T, 256>(ctx, pl, smem);
+    w_kernel_prologue<K, T, MAXT>(ctx, pl, smem);
     w_cta_init_bwd(pl, smem, threadIdx.x, blockDim.x);
     __syncthreads();
+    if (a.prof && blockIdx.x == 0 && ctx.team == 0) { ctx.prof = a.prof; if (ctx.tl == 0) ctx.prof[ctx.prof_i++] = clock64(); }
     w_backward_team<K, T>(ctx, pl, a, smem, ctx.team, blockIdx.x * pl.NT + ctx.team);
 }
 

@@ -19,18 +19,20 @@
 
 namespace recnext {
 
-struct WGrid {            // items of one stage, per plane: j = rb * strips + strip, j < ipp.  Plane g of the batch owns the
-    int strips, nrb, rpb; //   aligned lane group [g * LPP, (g + 1) * LPP) of its team; lane jl of the group takes
-    int ipp, rounds;      //   j = jl + round * LPP, round < rounds = ceil(ipp / LPP)
-    unsigned m_strips;    // magic for / strips
-};
+struct WGrid {            // items of one stage, per plane: j = rb * spr + strip (strip < strips), j < ipp = nrb * spr.
+    int strips, nrb, rpb; //   spr >= strips pads a row block to a multiple of 8 lanes, so that the 8 lanes of a 128-bit
+    int spr, ipp, rounds; //   shared-memory wavefront read ONE row (no bank conflicts between row blocks).  Plane g of the
+    unsigned m_spr;       //   batch owns the aligned lane group [g * LPP, (g + 1) * LPP) of its team; lane jl of the
+};                        //   group takes j = jl + round * LPP, round < rounds = ceil(ipp / LPP)
 
 struct WLevel {
     int H, W, pitch, rows;
     int offS;             // float offset of S_l inside a plane block (padded, interior at (+pad, +pad))
     int offX, offGT, offGS;  // bwd: x_l copy (1..L-1), grad wrt t_l, grad wrt s_l / total grad of x_l (1..L); -1 if absent
-    int tp;               // floats per row of this level's T buffer (unpadded rows)
+    int tp, toff;         // T buffer of this level: floats per row, column offset of the interior (2 + replicate border
+                          // on the aligned exact-2x bilinear path, else 0)
     int exact2x;          // level l-1 is exactly 2x this level (bilinear fast path)
+    int up_fast;          // exact2x, bilinear, even pad: 128-bit aligned read-modify-write of level l-1
     int tabY, tabX;       // byte offsets (table region) of IdxLam[H_{l-1}] / IdxLam[W_{l-1}]
     int gatY, gatX;       // bwd: GatherEntry[H_l] / GatherEntry[W_l]
     WGrid g1;             // stride-1 stencils on this level
@@ -54,6 +56,7 @@ struct WPlan {
     int grid;
     int esize, vec;
     unsigned magic_cpr, magic_H;
+    WGrid gp;             // unpack: "strips" = column pairs of level 0 (W even), rows split into blocks
     int use_tma;
     WLevel lv[kMaxLevel + 1];
     int plane_floats;     // floats per plane block (all padded level buffers)
@@ -70,11 +73,12 @@ struct WPlan {
     // cg = gt % n_cg for its whole life and takes images r, r + tpc, ... (r = gt / n_cg < tpc); otherwise (tpc = 1)
     // it walks over channel groups gt, gt + n_teams_total, ... and takes every image of each.
     int n_teams_total, tpc;
+    int dbg;              // timing experiments only: bit mask of stages to skip (RECNEXT_DBG), 0 in production
     int ws_partial_floats;  // bwd: [tpc][(L+2)][C][wstride] per-team filter-gradient partials
 };
 
 struct WPlanOptions {
-    int force_G = 0, force_TW = 0, force_NT = 0, force_no_tma = 0, max_warps = 0;
+    int force_G = 0, force_TW = 0, force_NT = 0, force_no_tma = 0, max_warps = 0, dbg = 0;
     int num_sms = 148;
     int smem_limit = 227 * 1024;
 };
@@ -82,14 +86,18 @@ struct WPlanOptions {
 RC_H WGrid w_grid(int LPP, int rows, int strips) {
     WGrid g;
     g.strips = strips;
-    int nrb = LPP / strips;  // row blocks so that one round keeps the plane's lanes busy
+    int spr = 1;
+    if (strips <= 4) { while (spr < strips) spr *= 2; }
+    else spr = rc_round_up(strips, 8);
+    g.spr = spr;
+    int nrb = LPP / spr;  // row blocks so that one round keeps the plane's lanes busy
     if (nrb < 1) nrb = 1;
     if (nrb > rows) nrb = rows;
     g.rpb = rc_div_up(rows, nrb);
     g.nrb = rc_div_up(rows, g.rpb);
-    g.ipp = g.nrb * g.strips;
+    g.ipp = g.nrb * g.spr;
     g.rounds = rc_div_up(g.ipp, LPP);
-    g.m_strips = rc_magic(g.strips);
+    g.m_spr = rc_magic(g.spr);
     return g;
 }
 
@@ -100,7 +108,7 @@ RC_H int w_make_plan(WPlan& pl, int B, int C, int H, int W, int K, int L, int mo
     if (H > 1023 || W > 1023) return 1;
     pl = WPlan();
     pl.B = B; pl.C = C; pl.H = H; pl.W = W; pl.K = K; pl.L = L; pl.mode = mode; pl.dtype = dtype; pl.wdtype = wdtype;
-    pl.has_bias = has_bias; pl.backward = backward;
+    pl.has_bias = has_bias; pl.backward = backward; pl.dbg = opt.dbg;
     pl.esize = dtype == 0 ? 4 : 2;
     const int pad = K / 2;
     pl.lv[0].H = H; pl.lv[0].W = W;
@@ -122,8 +130,10 @@ RC_H int w_make_plan(WPlan& pl, int B, int C, int H, int W, int K, int L, int mo
         if (l < L) { const int r2 = 2 * (pl.lv[l + 1].H - 1) + K; if (r2 > g.rows) g.rows = r2; }
         g.offS = off; off += g.rows * g.pitch;
         g.offX = g.offGT = g.offGS = -1;
-        g.tp = rc_round_up(g.W, 4);
         g.exact2x = (l >= 1 && pl.lv[l - 1].H == 2 * g.H && pl.lv[l - 1].W == 2 * g.W) ? 1 : 0;
+        g.up_fast = (g.exact2x && mode == 0 && (pad & 1) == 0) ? 1 : 0;
+        g.toff = g.up_fast ? 2 : 0;
+        g.tp = rc_round_up(g.W + 2 * g.toff, 4);
         g.magic_W = rc_magic(g.W);
         g.magic_HW = rc_magic(g.H * g.W);
     }
@@ -188,7 +198,7 @@ RC_H int w_make_plan(WPlan& pl, int B, int C, int H, int W, int K, int L, int mo
         if (gmax < 1) gmax = 1;
         for (int cand = 2; cand <= gmax && cand <= 32; cand *= 2) {
             if (C % cand != 0) break;
-            if (avail / team_bytes_for(cand, 1) < max_warps) break;
+            if (avail / team_bytes_for(cand, 1) < (max_warps >= 16 ? 12 : max_warps)) break;  // measured: 12 teams of 2 planes beat 16 of 1
             G = cand;
         }
     }
@@ -196,7 +206,7 @@ RC_H int w_make_plan(WPlan& pl, int B, int C, int H, int W, int K, int L, int mo
     int TW = 1;
     if (opt.force_TW) TW = opt.force_TW;
     else {
-        while (TW < 8 && (avail / team_bytes_for(G, TW)) * TW * 2 <= max_warps) TW *= 2;  // few big planes: several warps per plane
+        while (TW < 8 && (avail / team_bytes_for(G, TW)) * TW < 6 && TW * 2 <= max_warps) TW *= 2;  // big planes: >= 6 warps per SM
     }
     if (G > 32 * TW) return 1;
     const long tbz = team_bytes_for(G, TW);
@@ -236,6 +246,7 @@ RC_H int w_make_plan(WPlan& pl, int B, int C, int H, int W, int K, int L, int mo
 
     // ---- item grids ----
     pl.LPP = pl.team_lanes / G;
+    pl.gp = w_grid(pl.LPP, H, (W + 1) / 2);
     pl.lpp_shift = 0;
     while ((1 << pl.lpp_shift) < pl.LPP) ++pl.lpp_shift;
     for (int l = 0; l <= L; ++l) {
@@ -244,7 +255,8 @@ RC_H int w_make_plan(WPlan& pl, int B, int C, int H, int W, int K, int L, int mo
         if (l >= 1) {
             lg.g2 = lg.g1;
             const WLevel& ld = pl.lv[l - 1];
-            if (lg.exact2x && mode == 0) lg.gu = w_grid(pl.LPP, lg.H, rc_div_up(ld.W, kStripW));
+            if (lg.up_fast) lg.gu = w_grid(pl.LPP, lg.H, rc_div_up(ld.W + pad, kStripW));  // strips of PADDED columns
+            else if (lg.exact2x && mode == 0) lg.gu = w_grid(pl.LPP, lg.H, rc_div_up(ld.W, kStripW));
             else lg.gu = w_grid(pl.LPP, ld.H, rc_div_up(ld.W, kStripW));
             lg.gt = w_grid(pl.LPP, (ld.H + 1) / 2, (ld.W + 1) / 2);  // "strips" = column pairs, rows = row pairs
         }

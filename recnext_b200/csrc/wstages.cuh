@@ -16,9 +16,9 @@ struct WItem { int r0, c0, nrows; bool valid; };
 RC_HD WItem w_item(const WGrid& gr, int jl, int LPP, int round, int rows_total) {
     WItem it;
     const int j = jl + round * LPP;
-    it.valid = j < gr.ipp;
-    const int rb = rc_fastdiv(j, gr.m_strips);
-    it.c0 = (j - rb * gr.strips) * kStripW;
+    const int rb = rc_fastdiv(j, gr.m_spr), st = j - rb * gr.spr;
+    it.valid = j < gr.ipp && st < gr.strips;
+    it.c0 = st * kStripW;
     it.r0 = rb * gr.rpb;
     const int left = rows_total - it.r0;
     it.nrows = left < gr.rpb ? left : gr.rpb;
@@ -39,7 +39,7 @@ RC_HD void w_conv_s1(const float* __restrict__ src, int pitch, int Ho, const WGr
     const float bias = use_bias ? wslot[K * K] : 0.f;
     for (int rd = 0; rd < gr.rounds; ++rd) {
         const WItem it = w_item(gr, jl, LPP, rd, Ho);
-        if (!it.valid) break;
+        if (!it.valid) continue;
         const float* base = src + it.r0 * pitch + it.c0;
         float win[K][WL];
 #pragma unroll
@@ -74,7 +74,7 @@ RC_HD void w_conv_s2(const float* __restrict__ src, int pitch, int Ho, const WGr
     const float bias = use_bias ? wslot[K * K] : 0.f;
     for (int rd = 0; rd < gr.rounds; ++rd) {
         const WItem it = w_item(gr, jl, LPP, rd, Ho);
-        if (!it.valid) break;
+        if (!it.valid) continue;
         const float* base = src + 2 * it.r0 * pitch + 2 * it.c0;
         float win[K][WL];
 #pragma unroll
@@ -101,12 +101,40 @@ RC_HD void w_conv_s2(const float* __restrict__ src, int pitch, int Ho, const WGr
     }
 }
 
+// raw plane (element type T, unpadded, W even) -> padded fp32 interior.  An item is a column PAIR x a block of rows:
+// consecutive lanes read consecutive 4/8-byte words of a raw row and write consecutive 8-byte words.
+template <typename T>
+RC_HD void w_unpack_pairs(const T* __restrict__ raw, int H, int W, float* __restrict__ dst_interior, int pitch, const WGrid& gr,
+                          int jl, int LPP) {
+    for (int rd = 0; rd < gr.rounds; ++rd) {
+        const int j = jl + rd * LPP;
+        const int rb = rc_fastdiv(j, gr.m_spr), cp = j - rb * gr.spr;
+        if (j >= gr.ipp || cp >= gr.strips) continue;
+        const int r0 = rb * gr.rpb;
+        const int r1 = (r0 + gr.rpb) < H ? (r0 + gr.rpb) : H;
+        const T* s = raw + (long)r0 * W + 2 * cp;
+        float* d = dst_interior + r0 * pitch + 2 * cp;
+        for (int r = r0; r < r1; ++r) {
+            alignas(8) T v[2];
+            if (sizeof(T) == 4) *reinterpret_cast<float2*>(v) = *reinterpret_cast<const float2*>(s);
+            else *reinterpret_cast<float*>(v) = *reinterpret_cast<const float*>(s);
+            *reinterpret_cast<float2*>(d) = make_float2(Elem<T>::to_f(v[0]), Elem<T>::to_f(v[1]));
+            s += W; d += pitch;
+        }
+    }
+}
+
 // masked store of 4 results into a padded level buffer (interior coordinates row, c0); pads stay zero
 RC_HD void w_store_level(float* __restrict__ dst_interior, int pitch, int W, int row, int c0, const float (&v)[kStripW]) {
     float* d = dst_interior + row * pitch + c0;
     if (c0 + kStripW <= W) {
+        if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) {  // even pad and pitch: two aligned pairs
+            reinterpret_cast<float2*>(d)[0] = make_float2(v[0], v[1]);
+            reinterpret_cast<float2*>(d)[1] = make_float2(v[2], v[3]);
+        } else {
 #pragma unroll
-        for (int c = 0; c < kStripW; ++c) d[c] = v[c];
+            for (int c = 0; c < kStripW; ++c) d[c] = v[c];
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < kStripW; ++c)
@@ -133,7 +161,7 @@ RC_HD void w_up2x_add(float* __restrict__ dstS, int pitch, int Wd, const float* 
                       const WGrid& gr, int jl, int LPP) {
     for (int rd = 0; rd < gr.rounds; ++rd) {
         const WItem it = w_item(gr, jl, LPP, rd, Hl);  // rows = SOURCE rows, strips = destination strips
-        if (!it.valid) break;
+        if (!it.valid) continue;
         const int j0 = it.c0, cb = j0 >> 1, ca = cb > 0 ? cb - 1 : 0;
         const int cc = cb + 1 < Wl ? cb + 1 : Wl - 1, cd = cb + 2 < Wl ? cb + 2 : Wl - 1;
         const int m0 = it.r0, m1 = it.r0 + it.nrows;
@@ -169,12 +197,75 @@ RC_HD void w_up2x_add(float* __restrict__ dstS, int pitch, int Wd, const float* 
     }
 }
 
+// Aligned exact-2x bilinear path (even pad, K = 5): an item is 4 PADDED columns [4q, 4q+3] of level l-1 (16-byte
+// aligned, so the read-modify-write is one LDS.128 + STS.128 per row and consecutive lanes touch consecutive
+// banks) x a block of source rows.  The 4 columns are interior columns j0 = 4q - pad .. j0 + 3 and read source
+// columns a0 - 1 .. a0 + 2, a0 = j0 / 2: two aligned pairs of the T row, whose interior starts at column 2 behind
+// a replicate border of 2 (written by the conv epilogue, w_store_T_fast).  Cells outside the interior get +0.
+RC_HD void w_hrow2x_fast(float (&h)[kStripW], const float* __restrict__ trow) {
+    const float2 ab = *reinterpret_cast<const float2*>(trow);      // source columns a0 - 1, a0
+    const float2 cd = *reinterpret_cast<const float2*>(trow + 2);  // a0 + 1, a0 + 2
+    h[0] = fmaf(0.75f, ab.y, 0.25f * ab.x);
+    h[1] = fmaf(0.75f, ab.y, 0.25f * cd.x);
+    h[2] = fmaf(0.75f, cd.x, 0.25f * ab.y);
+    h[3] = fmaf(0.75f, cd.x, 0.25f * cd.y);
+}
+// dstS_padded: origin of the PADDED level l-1 buffer row `pad` (i.e. buffer + pad * pitch); T: plane's T buffer
+RC_HD void w_up2x_add_fast(float* __restrict__ dstS_rows, int pitch, int pad, int Wd, const float* __restrict__ T, int tp, int Hl,
+                           const WGrid& gr, int jl, int LPP) {
+    for (int rd = 0; rd < gr.rounds; ++rd) {
+        const WItem it = w_item(gr, jl, LPP, rd, Hl);  // rows = SOURCE rows, strips = groups of 4 padded columns
+        if (!it.valid) continue;
+        const int pc0 = it.c0;            // first padded column (multiple of 4)
+        const int j0 = pc0 - pad;         // first interior column (even)
+        const float* tcol = T + (j0 >> 1) + 1;  // T column of source a0 - 1 (interior offset 2): (j0/2 - 1) + 2
+        float msk[kStripW];
+#pragma unroll
+        for (int c = 0; c < kStripW; ++c) msk[c] = (j0 + c >= 0 && j0 + c < Wd) ? 1.f : 0.f;
+        const int m0 = it.r0, m1 = it.r0 + it.nrows;
+        float hp[kStripW], hc[kStripW], hn[kStripW];
+        w_hrow2x_fast(hp, tcol + (m0 > 0 ? m0 - 1 : 0) * tp);
+        w_hrow2x_fast(hc, tcol + m0 * tp);
+#pragma unroll
+        for (int c = 0; c < kStripW; ++c) { hp[c] *= msk[c]; hc[c] *= msk[c]; }
+        float* d = dstS_rows + 2 * m0 * pitch + pc0;
+        for (int m = m0; m < m1; ++m) {
+            w_hrow2x_fast(hn, tcol + (m + 1 < Hl ? m + 1 : Hl - 1) * tp);
+#pragma unroll
+            for (int c = 0; c < kStripW; ++c) hn[c] *= msk[c];
+            float4 u = *reinterpret_cast<float4*>(d);
+            float4 v = *reinterpret_cast<float4*>(d + pitch);
+            u.x += fmaf(0.75f, hc[0], 0.25f * hp[0]); u.y += fmaf(0.75f, hc[1], 0.25f * hp[1]);
+            u.z += fmaf(0.75f, hc[2], 0.25f * hp[2]); u.w += fmaf(0.75f, hc[3], 0.25f * hp[3]);
+            v.x += fmaf(0.75f, hc[0], 0.25f * hn[0]); v.y += fmaf(0.75f, hc[1], 0.25f * hn[1]);
+            v.z += fmaf(0.75f, hc[2], 0.25f * hn[2]); v.w += fmaf(0.75f, hc[3], 0.25f * hn[3]);
+            *reinterpret_cast<float4*>(d) = u;
+            *reinterpret_cast<float4*>(d + pitch) = v;
+            d += 2 * pitch;
+#pragma unroll
+            for (int c = 0; c < kStripW; ++c) { hp[c] = hc[c]; hc[c] = hn[c]; }
+        }
+    }
+}
+// conv epilogue of the fast path: 4 results of row `row` into T (interior at column 2) + the replicate border
+RC_HD void w_store_T_fast(float* __restrict__ T, int tp, int Wl, int row, int c0, const float (&v)[kStripW]) {
+    float* r = T + row * tp + 2 + c0;
+    reinterpret_cast<float2*>(r)[0] = make_float2(v[0], v[1]);  // columns >= Wl of the last strip are overwritten below
+    reinterpret_cast<float2*>(r)[1] = make_float2(v[2], v[3]);  // or never read
+    if (c0 == 0) { r[-2] = v[0]; r[-1] = v[0]; }
+    const int last = Wl - 1 - c0;  // 0..3 if this strip holds the last column
+    if (last >= 0 && last < kStripW) {
+        const float vl = last == 0 ? v[0] : (last == 1 ? v[1] : (last == 2 ? v[2] : v[3]));
+        r[last + 1] = vl; r[last + 2] = vl;
+    }
+}
+
 // generic sizes (7 -> 4, odd detection sizes) and nearest mode: table driven; items = 4 columns x rows of level l-1
 RC_HD void w_up_add(float* __restrict__ dstS, int pitch, int Hd, int Wd, const float* __restrict__ T, int tp, int Hl, int Wl,
                     const IdxLam* __restrict__ ytab, const IdxLam* __restrict__ xtab, int mode, const WGrid& gr, int jl, int LPP) {
     for (int rd = 0; rd < gr.rounds; ++rd) {
         const WItem it = w_item(gr, jl, LPP, rd, Hd);
-        if (!it.valid) break;
+        if (!it.valid) continue;
         const int j0 = it.c0;
         int x0[kStripW], x1[kStripW];
         float lx[kStripW];
@@ -258,7 +349,7 @@ RC_HD void w_wgrad_s1(const float* __restrict__ S, const float* __restrict__ G, 
     constexpr int PAD = K / 2;
     for (int rd = 0; rd < gr.rounds; ++rd) {
         const WItem it = w_item(gr, jl, LPP, rd, Ho);
-        if (!it.valid) break;
+        if (!it.valid) continue;
         const float* base = S + it.r0 * pitch + it.c0;
         const float* gbase = G + (it.r0 + PAD) * pitch + it.c0 + PAD;
         float win[K][WL];
@@ -294,7 +385,7 @@ RC_HD void w_wgrad_s2(const float* __restrict__ X, int xpitch, const float* __re
     constexpr int PAD = K / 2;
     for (int rd = 0; rd < gr.rounds; ++rd) {
         const WItem it = w_item(gr, jl, LPP, rd, Ho);
-        if (!it.valid) break;
+        if (!it.valid) continue;
         const float* base = X + 2 * it.r0 * xpitch + 2 * it.c0;
         const float* gbase = Gr + (it.r0 + PAD) * gpitch + it.c0 + PAD;
         float win[K][WL];
@@ -341,7 +432,8 @@ RC_HD void w_convT_s2(const float* __restrict__ Gr, int gpitch, const float* __r
     for (int rd = 0; rd < gr.rounds; ++rd) {
         const int j = jl + rd * LPP;
         if (j >= gr.ipp) break;
-        const int rb = rc_fastdiv(j, gr.m_strips), b = j - rb * gr.strips;
+        const int rb = rc_fastdiv(j, gr.m_spr), b = j - rb * gr.spr;
+        if (b >= gr.strips) continue;
         const int a0 = rb * gr.rpb, a1 = (a0 + gr.rpb) < nrp ? (a0 + gr.rpb) : nrp;
         const float* gp = Gr + (a0 + LO + PAD) * gpitch + (b + LO + PAD);
         float gw[NW][NW];

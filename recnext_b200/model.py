@@ -43,6 +43,28 @@ class DropPath(nn.Module):
         return x * mask.div_(keep)
 
 
+class PointwiseConv2d(nn.Conv2d):
+    """1x1 convolution with the ``nn.Conv2d`` parameters / state_dict, evaluated as ONE batched GEMM on the NCHW
+    tensor: y[b] = W [Cout, Cin] @ x[b] [Cin, H*W] (+ bias).  cuDNN's bf16 1x1 path converts NCHW -> NHWC and back
+    around every call (31 % of the M3 inference step in profiles/r1_launches_bench_step.txt); the RecConv path and
+    BatchNorm want NCHW, so the GEMM is done in that layout instead.  Library GEMM (cuBLAS): plumbing, not a kernel
+    of this repo.  Falls back to F.conv2d for anything that is not a plain contiguous 1x1 case."""
+
+    def forward(self, x):
+        if (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0) and self.groups == 1 and x.dim() == 4
+                and x.is_contiguous() and not torch.jit.is_tracing()):
+            B, C, H, W = x.shape
+            w = self.weight.view(self.out_channels, C)
+            if torch.is_autocast_enabled() and x.is_cuda:
+                dt = torch.get_autocast_dtype("cuda")
+                x, w = x.to(dt), w.to(dt)
+            y = torch.matmul(w, x.view(B, C, H * W))
+            if self.bias is not None:
+                y = y + self.bias.to(y.dtype).view(1, -1, 1)
+            return y.view(B, self.out_channels, H, W)
+        return super().forward(x)
+
+
 class ConvNorm(nn.Sequential):
     """conv (no bias) + BatchNorm2d; ``fuse()`` folds the running statistics into a biased conv."""
 
@@ -58,8 +80,9 @@ class ConvNorm(nn.Sequential):
         shift = bn.bias - scale * bn.running_mean
         if conv.bias is not None:
             shift = shift + scale * conv.bias
-        out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
-                        conv.groups, bias=True, device=conv.weight.device, dtype=conv.weight.dtype)
+        cls = nn.Conv2d  # (PointwiseConv2d measured slower than cuDNN's path on B200: cuBLAS picks legacy kernels for this layout)
+        out = cls(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
+                  conv.groups, bias=True, device=conv.weight.device, dtype=conv.weight.dtype)
         out.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
         out.bias.copy_(shift)
         return out

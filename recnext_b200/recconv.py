@@ -192,7 +192,11 @@ class RecConv2d(nn.Module):
         weights, biases = self._param_lists()
         if torch.is_autocast_enabled() and x.is_cuda:
             x = x.to(torch.get_autocast_dtype("cuda"))  # conv2d is an autocast-to-low-precision op in the reference path
-        return _RecConvFn.apply(x, self.kernel_size, self.level, self.mode, len(biases), *weights, *biases)
+        # the kernels work on NCHW planes; a channels_last input is transposed once and the result is handed back in
+        # the caller's memory format (what nn.Conv2d does), so a channels_last model keeps its 1x1 convs transpose-free
+        channels_last = x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+        y = _RecConvFn.apply(x, self.kernel_size, self.level, self.mode, len(biases), *weights, *biases)
+        return y.contiguous(memory_format=torch.channels_last) if channels_last else y
 
     def extra_repr(self):
         return f"level={self.level}, mode={self.mode!r}, kernel_size={self.kernel_size}"

@@ -1,20 +1,43 @@
 """Samples / instructions / shared wavefronts per named source region.  python tools/ncu_regions.py rep"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
-REG = [("wstages.cuh", 13, 27, "item decode"), ("wstages.cuh", 32, 64, "conv_s1"), ("wstages.cuh", 66, 102, "conv_s2"),
-       ("wstages.cuh", 104, 116, "store_level"), ("wstages.cuh", 117, 170, "up2x"), ("wstages.cuh", 171, 215, "up generic"),
-       ("wstages.cuh", 216, 235, "store_global"), ("wstages.cuh", 236, 260, "up_bwd gather"), ("wstages.cuh", 261, 300, "wgrad_s1"),
-       ("wstages.cuh", 301, 345, "wgrad_s2"), ("wstages.cuh", 346, 420, "convT_s2"),
-       ("recconv_stages.cuh", 84, 93, "load_row"), ("recconv_stages.cuh", 94, 131, "unpack"), ("recconv_stages.cuh", 132, 150, "load_filter"),
-       ("recconv_stages.cuh", 59, 83, "elem cvt")]
+WANT = sys.argv[2] if len(sys.argv) > 2 else ""
+fn = ""
+import os, re
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def regions_of(fname):
+    """(file, first line, last line, function name) for every RC_HD / __device__ function of a csrc header"""
+    path = os.path.join(ROOT, "recnext_b200", "csrc", fname)
+    lines = open(path).read().split("\n")
+    starts = []
+    for i, ln in enumerate(lines, 1):
+        m = re.match(r"^(?:RC_HD|RC_H|__device__ __forceinline__|static)\s+[\w:<>\s\*&]*?\b(\w+)\s*\(", ln)
+        if m and not ln.startswith("    "):
+            j = i
+            while j > 1 and lines[j - 2].startswith("template"):
+                j -= 1
+            starts.append((j, m.group(1)))
+    out = []
+    for k, (ln, nm) in enumerate(starts):
+        end = starts[k + 1][0] - 1 if k + 1 < len(starts) else len(lines)
+        out.append((fname, ln, end, nm))
+    return out
+
+
+REG = []
+for f in ("wstages.cuh", "recconv_stages.cuh", "wbody.cuh", "wdevice.cuh", "recconv_device.cuh"):
+    REG += regions_of(f)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
 hdr = None; agg = {}
 for r in csv.reader(io.StringIO(src)):
     if not r: continue
     if r[0] == "File Path": f = r[1].split('/')[-1]; continue
+    if r[0] == "Function Name": fn = r[1]; continue
     if r[0] == "Line No": hdr = {c: i for i, c in enumerate(r)}; continue
-    if hdr is None or r[0] == "" or r[0] == "Function Name": continue
-    g = lambda c: int(r[hdr[c]]) if r[hdr[c]].isdigit() else 0
+    if hdr is None or r[0] == "" or (WANT and WANT not in fn): continue
+    g = lambda c: int(r[hdr[c]]) if (c in hdr and r[hdr[c]].isdigit()) else 0
     ln = int(r[0]); name = f
     for (ff, a, b, nm) in REG:
         if ff == f and a <= ln <= b: name = nm
