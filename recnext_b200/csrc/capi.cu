@@ -9,9 +9,11 @@
 #include "../../include/recnext_b200.h"
 #include "recconv_body.cuh"
 #include "wplan.h"
+#include "mplan.h"
 #include <stdlib.h>
 
 namespace recnext {
+cudaError_t m_launch(const MPlan&, const KernelArgs&, cudaStream_t);  // recconv_m5.cu: tensor-core forward
 template <int K, typename T, bool BWD> cudaError_t w_launch(const WPlan&, const KernelArgs&, cudaStream_t);
 typedef cudaError_t (*w_launch_fn)(const WPlan&, const KernelArgs&, cudaStream_t);
 #define W_DECLARE_K(K)                                                                                           \
@@ -151,6 +153,31 @@ static int make_wplan(const recconv_desc* d, bool bwd, WPlan& pl) {
     return w_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, bwd ? 1 : 0, opt) == 0 ? 0 : 1;
 }
 
+// RECNEXT_PATH=fma keeps the FP32-FMA kernels for 16-bit activations too (A/B measurements, tests of both paths)
+static bool fma_forced() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RECNEXT_PATH"); v = (e && (strcmp(e, "fma") == 0 || strcmp(e, "legacy") == 0)) ? 1 : 0; }
+    return v == 1;
+}
+// while the tensor-core forward is being tuned it is opt-in: RECNEXT_PATH=mma
+static bool mma_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RECNEXT_PATH"); v = (e && strcmp(e, "mma") == 0) ? 1 : 0; }
+    return v == 1;
+}
+// 0: tensor-core forward plan made (16-bit activations, k = 5); 1: not eligible
+static int make_mplan(const recconv_desc* d, MPlan& pl) {
+    if (fma_forced() || !mma_enabled() || d->k != 5 || !(d->dtype == RECNEXT_BF16 || d->dtype == RECNEXT_F16)) return 1;
+    MPlanOptions opt;
+    opt.num_sms = device_sms();
+    if (const char* e = getenv("RECNEXT_MG")) opt.force_G = atoi(e);
+    if (const char* e = getenv("RECNEXT_MTW")) opt.force_TW = atoi(e);
+    if (const char* e = getenv("RECNEXT_MNT")) opt.force_NT = atoi(e);
+    if (const char* e = getenv("RECNEXT_MNOTMA")) opt.force_no_tma = atoi(e);
+    if (const char* e = getenv("RECNEXT_MDBG")) opt.dbg = atoi(e);
+    return m_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, opt) == 0 ? 0 : 1;
+}
+
 static int fill_args(const recconv_desc* d, const recconv_params* p, KernelArgs& a) {
     if (!p) return fail(RECNEXT_EINVAL, "recconv: null params");
     memset(&a, 0, sizeof(a));
@@ -195,6 +222,13 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
     KernelArgs a;
     if (int rc = fill_args(d, p, a)) return rc;
     a.x = x; a.out = y;
+    MPlan mp;
+    if ((((uintptr_t)x | (uintptr_t)y) & 3) == 0 && make_mplan(d, mp) == 0) {
+        if (((uintptr_t)x & 15) != 0) mp.use_tma = 0;  // bulk copies need 16-byte aligned sources (raw buffer stays allocated)
+        const cudaError_t e = m_launch(mp, a, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward(mma): %s", cudaGetErrorString(e));
+        return RECNEXT_OK;
+    }
     WPlan wp;
     if (make_wplan(d, false, wp) == 0) {
         a.prof = prof_buffer();
@@ -278,6 +312,15 @@ RECNEXT_API int recnext_debug_prof(long long* host_out, int n) {
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen) {
     if (int rc = check_desc(d)) return rc;
     if (!buf || !buflen) return fail(RECNEXT_EINVAL, "recconv_plan_describe: null buffer");
+    MPlan mp;
+    if (!backward && make_mplan(d, mp) == 0) {
+        snprintf(buf, buflen,
+                 "fwd tensor-core k=5 L=%d [%d,%d,%d,%d] planes/batch=%d warps/team=%d teams/CTA=%d threads=%d grid=%d smem=%d B team=%d B "
+                 "plane=%d B frag-regs/channel=%d tma=%d",
+                 mp.L, mp.B, mp.C, mp.H, mp.W, mp.G, mp.TW, mp.NTEAM, mp.threads, mp.grid, mp.smem_bytes, mp.team_bytes, mp.plane_bytes,
+                 mp.nregs, mp.use_tma);
+        return RECNEXT_OK;
+    }
     WPlan wp;
     if (make_wplan(d, backward != 0, wp) == 0) {
         snprintf(buf, buflen,

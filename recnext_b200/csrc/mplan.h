@@ -1,0 +1,167 @@
+// mplan.h — launch plan of the TENSOR-CORE RecConv forward (16-bit activations, k = 5).
+//
+// Why.  Measured on B200 (tools/mma_probe.cu): scalar FP32 FMA tops out at 31.6 TFMA/s (FFMA2 gives nothing more),
+// while the warp-level HMMA path sustains 278 TMAC/s.  The fused block needs ~48 FMA per element, so on the FMA
+// pipe a bf16 forward cannot pass ~33 % of the HBM roofline.  Here every depthwise 5x5 stencil is evaluated as five
+// banded-Toeplitz matrix products on the tensor cores:
+//     out[i, 8q + n] = sum_r  sum_k  S[i + r, 8q + k] * Bt_r[k, n],     Bt_r[k, n] = w[r, k - n]  (0 <= k - n <= 4)
+// i.e. one m16n8k16 MMA per (16 output rows, 8 output columns, filter row r): A = 16 image rows x 16 columns read
+// with ldmatrix straight out of the padded level buffer (a filter row is just another row address), B = the
+// channel's Toeplitz band (two registers per filter row, precomputed per channel), fp32 accumulators.  The stride-2
+// `down` filter is the same with Bt_r[k, n] = w[r, k - 2n] over 24 columns (m16n8k16 + m16n8k8).  3.7x more MACs
+// than the direct form, on a pipe that is 8.8x faster.  Products of 16-bit operands are exact in fp32 and every
+// intermediate is rounded to the activation dtype exactly where the reference's autocast graph rounds it
+// (conv outputs, f + x, interpolate), so this path tracks the reference's own bf16 numerics (model/recnext.py:24-34).
+//
+// Data layout.  A CTA serves one CHANNEL GROUP (G consecutive channels) at a time and walks over images; its
+// per-channel Toeplitz fragments live in one table shared by all warps.  A TEAM (TW warps) owns a batch of G planes:
+// every pyramid level is a padded 16-bit buffer in the team's slice (interior at (+2, +2), zero borders written
+// once), rows split by PARITY into two arrays so that both the stride-1 (8 consecutive rows) and the stride-2
+// (8 alternate rows) ldmatrix row sets are bank-conflict free: row pitch = odd number of 16-byte chunks, odd array
+// offset = 4 chunks mod 8.  Raw planes arrive by one TMA bulk copy per batch (prefetched a whole batch ahead).
+#pragma once
+#include "recconv_plan.h"
+
+namespace recnext {
+
+struct MLevel {
+    int H, W;
+    int NT, MT;          // n-tiles (8 columns) and m-tiles (16 rows) of this level
+    int ntc;             // n-tiles handled per pass of the tile routine (1, 2, 4, 7)
+    int pitchB;          // row pitch in bytes (odd multiple of 16)
+    int off, parDelta;   // byte offset of the even-row array inside a plane block; distance to the odd-row array
+    int tpB;             // l >= 1: row pitch (bytes) of the T buffer of this level; interior at element 2
+    int tabY, tabX;      // l >= 1: byte offsets (table region) of IdxLam[H_{l-1}] / IdxLam[W_{l-1}]
+    int exact2x;         // level l-1 is exactly 2x this level
+    int up_shift;        // l >= 1: up-add lane mapping over level l-1: lanes per row group = 1 << up_shift
+};
+
+struct MPlan {
+    int B, C, H, W, L, mode, dtype, wdtype, has_bias;
+    int G, TW, NTEAM, threads, team_lanes;
+    int n_cg;
+    int use_tma;
+    int rp_shift;        // repack lane mapping (column pairs of level 0, or columns if W is odd)
+    MLevel lv[kMaxLevel + 1];
+    int plane_bytes;     // one plane block: all level buffers + T
+    int offT;            // byte offset of the T buffer inside a plane block
+    int raw_bytes;       // G raw planes
+    int off_raw, team_bytes;
+    int nregs;           // Toeplitz fragment registers per channel: 20 (down) + 10 per conv
+    int smBar, smTab, smFrag, smBias, smTeams, smem_bytes;
+    int grid;
+    int dbg;
+};
+
+struct MPlanOptions {
+    int force_G = 0, force_TW = 0, force_NT = 0, force_no_tma = 0, max_warps = 16, dbg = 0;
+    int num_sms = 148;
+    int smem_limit = 227 * 1024;
+};
+
+RC_H int m_pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+RC_H int m_log2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+// 0 ok; 1 not eligible / does not fit (caller uses the FMA kernels); 2 bad arguments
+RC_H int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mode, int dtype, int wdtype, int has_bias,
+                     const MPlanOptions& opt) {
+    if (B < 1 || C < 1 || H < 1 || W < 1 || L < 0 || L > kMaxLevel) return 2;
+    if (K != 5 || !(dtype == 1 || dtype == 2)) return 1;
+    if (H > 1023 || W > 1023) return 1;
+    pl = MPlan();
+    pl.B = B; pl.C = C; pl.H = H; pl.W = W; pl.L = L; pl.mode = mode; pl.dtype = dtype; pl.wdtype = wdtype; pl.has_bias = has_bias;
+    pl.dbg = opt.dbg;
+    pl.lv[0].H = H; pl.lv[0].W = W;
+    for (int l = 1; l <= L; ++l) { pl.lv[l].H = rc_down_size(pl.lv[l - 1].H, 5); pl.lv[l].W = rc_down_size(pl.lv[l - 1].W, 5); }
+    for (int l = 0; l <= L; ++l) {
+        MLevel& g = pl.lv[l];
+        g.NT = rc_div_up(g.W, 8); g.MT = rc_div_up(g.H, 16);
+        g.ntc = g.NT <= 1 ? 1 : (g.NT == 2 ? 2 : (g.NT <= 4 ? 4 : 7));
+    }
+    // level buffers
+    int off = 0, tmax = 0;
+    for (int l = 0; l <= L; ++l) {
+        MLevel& g = pl.lv[l];
+        int kb = g.NT + 1;                                        // as the input of a stride-1 conv
+        if (l < L && 2 * pl.lv[l + 1].NT + 1 > kb) kb = 2 * pl.lv[l + 1].NT + 1;  // as the input of `down`
+        if ((g.W + 4 + 7) / 8 > kb) kb = (g.W + 4 + 7) / 8;
+        if ((kb & 1) == 0) ++kb;
+        g.pitchB = 16 * kb;
+        const int rows = g.H + 4, nE = (rows + 1) / 2, nO = rows / 2;
+        g.off = off;
+        int d = nE * g.pitchB + 16;                                // + slack for the one-chunk over-read of a paired load
+        while (((d / 16) & 7) != 4) d += 16;
+        g.parDelta = d;
+        off += d + nO * g.pitchB + 16;
+        off = rc_round_up(off, 128);
+        g.exact2x = (l >= 1 && pl.lv[l - 1].H == 2 * g.H && pl.lv[l - 1].W == 2 * g.W) ? 1 : 0;
+        if (l >= 1) {
+            g.tpB = rc_round_up((g.W + 4) * 2, 4);
+            if (g.H * g.tpB > tmax) tmax = g.H * g.tpB;
+        }
+    }
+    pl.offT = off;
+    off += rc_round_up(tmax, 128);
+    pl.plane_bytes = off;
+
+    // tables shared by the CTA
+    int tb = 0;
+    for (int l = 1; l <= L; ++l) {
+        pl.lv[l].tabY = tb; tb += 8 * pl.lv[l - 1].H;
+        pl.lv[l].tabX = tb; tb += 8 * pl.lv[l - 1].W;
+    }
+    tb = rc_round_up(tb, 128);
+
+    // planes per batch: the raw batch must be a whole number of 16-byte chunks for the bulk copy, and tiny planes
+    // are batched to amortise the per-batch overhead
+    const int plane_raw = H * W * 2;
+    int G = 1;
+    if (opt.force_G) G = opt.force_G;
+    else {
+        const int frag_bytes = (20 + 10 * (L + 1)) * 128;          // per channel
+        while (G < 16 && C % (2 * G) == 0 && (((G * plane_raw) % 16) != 0 || (G * H * W < 512 && 2 * G * frag_bytes <= 48 * 1024))) G *= 2;
+    }
+    if (G < 1 || C % G != 0) return 1;
+    pl.G = G; pl.n_cg = C / G;
+    pl.raw_bytes = G * plane_raw;
+    pl.use_tma = (!opt.force_no_tma && (pl.raw_bytes % 16) == 0 && pl.raw_bytes <= 64 * 1024) ? 1 : 0;
+    pl.nregs = 20 + 10 * (L + 1);
+
+    pl.off_raw = G * pl.plane_bytes;
+    pl.team_bytes = pl.off_raw + (pl.use_tma ? rc_round_up(pl.raw_bytes, 128) : 0);
+    pl.smBar = 0;
+    pl.smTab = 256;
+    pl.smFrag = pl.smTab + tb;
+    pl.smBias = pl.smFrag + G * pl.nregs * 128;
+    pl.smTeams = rc_round_up(pl.smBias + G * (L + 2) * 4, 128);
+    const long avail = (long)opt.smem_limit - pl.smTeams;
+    if (avail < pl.team_bytes) return 1;
+    const int fit = (int)(avail / pl.team_bytes);
+    int max_warps = opt.max_warps > 16 ? 16 : opt.max_warps;
+    if (max_warps < 1) max_warps = 1;
+    int TW = 1;
+    if (opt.force_TW) TW = opt.force_TW;
+    else { while (TW < 8 && fit * TW < 8 && TW * 2 <= max_warps) TW *= 2; }
+    int NTEAM = fit;
+    if (NTEAM * TW > max_warps) NTEAM = max_warps / TW;
+    if (TW > 1 && NTEAM > 15) NTEAM = 15;   // one named barrier per team
+    if (opt.force_NT) NTEAM = opt.force_NT;
+    if (NTEAM < 1 || NTEAM > fit || NTEAM * TW > 16 || NTEAM > 16) return 1;
+    pl.TW = TW; pl.NTEAM = NTEAM; pl.team_lanes = 32 * TW; pl.threads = 32 * TW * NTEAM;
+    pl.smem_bytes = pl.smTeams + NTEAM * pl.team_bytes;
+    if (pl.smem_bytes > opt.smem_limit) return 1;
+
+    // lane mappings of the element-wise stages: (row group, column pair)
+    auto shift_for = [&](int pairs) { int p = m_pow2_ceil(pairs); if (p > pl.team_lanes) p = pl.team_lanes; return m_log2(p); };
+    pl.rp_shift = shift_for((W & 1) ? W : W / 2);
+    for (int l = 1; l <= L; ++l) pl.lv[l].up_shift = shift_for((pl.lv[l - 1].W + 1) / 2);
+
+    const long total = (long)pl.n_cg * B;
+    long grid = opt.num_sms;
+    if (total < grid * NTEAM) grid = (total + NTEAM - 1) / NTEAM;
+    if (grid < 1) grid = 1;
+    pl.grid = (int)grid;
+    return 0;
+}
+
+}  // namespace recnext
