@@ -317,7 +317,7 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
         snprintf(buf, buflen,
                  "fwd tensor-core k=5 L=%d [%d,%d,%d,%d] planes/batch=%d warps/team=%d teams/CTA=%d threads=%d grid=%d smem=%d B team=%d B "
                  "plane=%d B frag-regs/channel=%d tma=%d",
-                 mp.L, mp.B, mp.C, mp.H, mp.W, mp.G, mp.TW, mp.NTEAM, mp.threads, mp.grid, mp.smem_bytes, mp.team_bytes, mp.plane_bytes,
+                 mp.L, mp.B, mp.C, mp.H, mp.W, mp.G, mp.TW, mp.NTEAM, mp.threads, mp.grid, mp.smem_bytes, mp.team_bytes, mp.l0_bytes + mp.upper_bytes,
                  mp.nregs, mp.use_tma);
         return RECNEXT_OK;
     }

@@ -7,6 +7,8 @@
 #include <cuda_fp16.h>
 #include "recconv_device.cuh"  // mbarrier / cp.async.bulk wrappers, KernelArgs, IdxLam tables
 #include "mplan.h"
+#include <string.h>
+#include <type_traits>
 
 namespace recnext {
 
@@ -18,6 +20,12 @@ template <> struct MmaT<__nv_bfloat16> {
     }
     static __device__ __forceinline__ float2 unpack(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
     static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+    static __device__ __forceinline__ float lo(uint32_t u) { return __uint_as_float(u << 16); }       // element 0 of a pair
+    static __device__ __forceinline__ float one(uint32_t h) { return __uint_as_float(h << 16); }      // a zero-extended element
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {                          // round(a + b) per element
+        __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
     static __device__ __forceinline__ void mma16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -34,6 +42,12 @@ template <> struct MmaT<__half> {
     }
     static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
     static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
+    static __device__ __forceinline__ float lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+    static __device__ __forceinline__ float one(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)h)); }
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+        __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
     static __device__ __forceinline__ void mma16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -72,103 +86,106 @@ struct MBuf {
 
 // ---------------------------------------------------------------------------------------------------------
 // 16 output rows [i0, i0+16) x NTC n-tiles [q0, q0+NTC) of a stride-1 5x5 depthwise conv of buffer `in`.
-// bfr: this lane's column of the channel's Toeplitz fragment table for this conv (register (r, j) at bfr[(2r+j)*32]).
+// bfr: shared address of this lane's column of the channel's Toeplitz fragments for this conv (register (r, j) at
+// bfr + (2r+j)*128).  FULL: all NTC n-tiles exist (no guards: straight-line code, no reconvergence barriers).
+// Fragment rows 0..7 are image rows i0 + 0, 2, .., 14 and fragment rows 8..15 are i0 + 1, 3, .., 15: the 8 rows of
+// every 8x8 ldmatrix phase then have ONE parity for every filter row r, i.e. they are consecutive rows of one
+// parity array (odd chunk pitch): conflict free.
 // epi(q, acc): acc[0..1] = (row i0 + 2(lane/4), columns 8q + 2(lane%4) + {0,1}), acc[2..3] = same columns of the next row.
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int NTC, class Epi>
-__device__ __forceinline__ void m_conv_s1_tile(const MBuf& in, int i0, int q0, int nt, const uint32_t* __restrict__ bfr, float bias,
-                                               int lane, Epi epi) {
+template <typename T, int NTC, bool FULL, class Epi>
+__device__ __forceinline__ void m_conv_s1_tile(const MBuf& in, int i0, int q0, int nt, uint32_t bfr, float bias, int lane, Epi epi) {
     float acc[NTC][4];
 #pragma unroll
     for (int q = 0; q < NTC; ++q) { acc[q][0] = bias; acc[q][1] = bias; acc[q][2] = bias; acc[q][3] = bias; }
-    // fragment rows 0..7 are image rows i0 + 0, 2, .., 14 and fragment rows 8..15 are i0 + 1, 3, .., 15: the 8 rows of
-    // every 8x8 ldmatrix phase then have ONE parity for every filter row r, i.e. they are consecutive rows of one
-    // parity array (odd chunk pitch): conflict free.  A thread ends up with the 2x2 block (rows i0 + 2g + {0,1}).
-    const int lrow = 2 * (lane & 7) + ((lane >> 3) & 1), lkb = lane >> 4;
+    const int lrow = 2 * (lane & 7) + ((lane >> 3) & 1);
+    const uint32_t lcol = (uint32_t)(q0 + (lane >> 4)) * 16u;
     const int rowMax = in.H + 3;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         int rr = i0 + lrow + r;
         rr = rr < rowMax ? rr : rowMax;
-        const uint32_t arow = in.row(rr) + (uint32_t)q0 * 16u;
+        const uint32_t arow = in.row(rr) + lcol;
         uint32_t A[NTC + 1][2];
 #pragma unroll
         for (int kb = 0; kb + 1 <= NTC; kb += 2)
-            if (q0 + kb <= nt) m_ldsm4(A[kb][0], A[kb][1], A[kb + 1][0], A[kb + 1][1], arow + (uint32_t)(kb + lkb) * 16u);
+            if (FULL || q0 + kb <= nt) m_ldsm4(A[kb][0], A[kb][1], A[kb + 1][0], A[kb + 1][1], arow + (uint32_t)kb * 16u);
         if (((NTC + 1) & 1) != 0) {
-            if (q0 + NTC <= nt) m_ldsm2(A[NTC][0], A[NTC][1], arow + (uint32_t)NTC * 16u);
+            if (FULL || q0 + NTC <= nt) m_ldsm2(A[NTC][0], A[NTC][1], arow - (uint32_t)(lane >> 4) * 16u + (uint32_t)NTC * 16u);
         }
-        const uint32_t b0 = bfr[(2 * r) * 32], b1 = bfr[(2 * r + 1) * 32];
+        const uint32_t b0 = m_lds32(bfr + (2 * r) * 128), b1 = m_lds32(bfr + (2 * r + 1) * 128);
 #pragma unroll
         for (int q = 0; q < NTC; ++q)
-            if (q0 + q < nt) MmaT<T>::mma16(acc[q], A[q][0], A[q][1], A[q + 1][0], A[q + 1][1], b0, b1);
+            if (FULL || q0 + q < nt) MmaT<T>::mma16(acc[q], A[q][0], A[q][1], A[q + 1][0], A[q + 1][1], b0, b1);
     }
 #pragma unroll
     for (int q = 0; q < NTC; ++q)
-        if (q0 + q < nt) epi(q0 + q, acc[q]);
+        if (FULL || q0 + q < nt) epi(q0 + q, acc[q]);
 }
 
 // 16 output rows x NTC n-tiles of the stride-2 5x5 depthwise conv (`down`): input rows 2i + r, columns 16q + k, k < 24.
-// bfr: register (r, j) at bfr[(4r+j)*32], j = 0,1 -> k 0..15 (m16n8k16), j = 2 -> k 16..23 (m16n8k8).
-template <typename T, int NTC, class Epi>
-__device__ __forceinline__ void m_conv_s2_tile(const MBuf& in, int i0, int q0, int nt, const uint32_t* __restrict__ bfr, float bias,
-                                               int lane, Epi epi) {
+// bfr: register (r, j) at bfr + (4r+j)*128, j = 0,1 -> k 0..15 (m16n8k16), j = 2 -> k 16..23 (m16n8k8).
+// epi(q, acc): acc[0..1] = (row i0 + lane/4, columns 8q + 2(lane%4) + {0,1}), acc[2..3] = same columns of row + 8.
+template <typename T, int NTC, bool FULL, class Epi>
+__device__ __forceinline__ void m_conv_s2_tile(const MBuf& in, int i0, int q0, int nt, uint32_t bfr, float bias, int lane, Epi epi) {
     float acc[NTC][4];
 #pragma unroll
     for (int q = 0; q < NTC; ++q) { acc[q][0] = bias; acc[q][1] = bias; acc[q][2] = bias; acc[q][3] = bias; }
-    const int lrow = lane & 15, lkb = lane >> 4;
+    const int lrow = lane & 15;
+    const uint32_t lcol = (uint32_t)(2 * q0 + (lane >> 4)) * 16u;
     const int rowMax = in.H + 3;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
         int rr = 2 * (i0 + lrow) + r;
         rr = rr < rowMax ? rr : rowMax;
-        const uint32_t arow = in.row(rr) + (uint32_t)q0 * 32u;
+        const uint32_t arow = in.row(rr) + lcol;
         uint32_t A[2 * NTC + 1][2];
 #pragma unroll
         for (int p = 0; p < NTC; ++p)
-            if (q0 + p <= nt) m_ldsm4(A[2 * p][0], A[2 * p][1], A[2 * p + 1][0], A[2 * p + 1][1], arow + (uint32_t)(2 * p + lkb) * 16u);
-        if (q0 + NTC <= nt) m_ldsm2(A[2 * NTC][0], A[2 * NTC][1], arow + (uint32_t)(2 * NTC) * 16u);
-        const uint32_t b0 = bfr[(4 * r) * 32], b1 = bfr[(4 * r + 1) * 32], b2 = bfr[(4 * r + 2) * 32];
+            if (FULL || q0 + p <= nt) m_ldsm4(A[2 * p][0], A[2 * p][1], A[2 * p + 1][0], A[2 * p + 1][1], arow + (uint32_t)(2 * p) * 16u);
+        if (FULL || q0 + NTC <= nt) m_ldsm2(A[2 * NTC][0], A[2 * NTC][1], arow - (uint32_t)(lane >> 4) * 16u + (uint32_t)(2 * NTC) * 16u);
+        const uint32_t b0 = m_lds32(bfr + (4 * r) * 128), b1 = m_lds32(bfr + (4 * r + 1) * 128), b2 = m_lds32(bfr + (4 * r + 2) * 128);
 #pragma unroll
         for (int q = 0; q < NTC; ++q)
-            if (q0 + q < nt) {
+            if (FULL || q0 + q < nt) {
                 MmaT<T>::mma16(acc[q], A[2 * q][0], A[2 * q][1], A[2 * q + 1][0], A[2 * q + 1][1], b0, b1);
                 MmaT<T>::mma8(acc[q], A[2 * q + 2][0], A[2 * q + 2][1], b2);
             }
     }
 #pragma unroll
     for (int q = 0; q < NTC; ++q)
-        if (q0 + q < nt) epi(q0 + q, acc[q]);
+        if (FULL || q0 + q < nt) epi(q0 + q, acc[q]);
 }
 
-template <typename T, bool S2, class Epi>
-__device__ __forceinline__ void m_conv_rows(const MBuf& in, int ntc, int i0, int nt, const uint32_t* __restrict__ bfr, float bias, int lane,
-                                            Epi epi) {
-    if (S2) {
-        switch (ntc) {
-            case 1: m_conv_s2_tile<T, 1>(in, i0, 0, nt, bfr, bias, lane, epi); break;
-            case 2: m_conv_s2_tile<T, 2>(in, i0, 0, nt, bfr, bias, lane, epi); break;
-            case 4: m_conv_s2_tile<T, 4>(in, i0, 0, nt, bfr, bias, lane, epi); break;
-            default: for (int q0 = 0; q0 < nt; q0 += 7) m_conv_s2_tile<T, 7>(in, i0, q0, nt, bfr, bias, lane, epi); break;
-        }
-    } else {
-        switch (ntc) {
-            case 1: m_conv_s1_tile<T, 1>(in, i0, 0, nt, bfr, bias, lane, epi); break;
-            case 2: m_conv_s1_tile<T, 2>(in, i0, 0, nt, bfr, bias, lane, epi); break;
-            case 4: m_conv_s1_tile<T, 4>(in, i0, 0, nt, bfr, bias, lane, epi); break;
-            default: for (int q0 = 0; q0 < nt; q0 += 7) m_conv_s1_tile<T, 7>(in, i0, q0, nt, bfr, bias, lane, epi); break;
-        }
+template <typename T, bool S2, int NTC, class Epi>
+__device__ __forceinline__ void m_conv_chunks(const MBuf& in, int i0, int nt, uint32_t bfr, float bias, int lane, Epi epi) {
+    int q0 = 0;
+    for (; q0 + NTC <= nt; q0 += NTC) {
+        if (S2) m_conv_s2_tile<T, NTC, true>(in, i0, q0, nt, bfr, bias, lane, epi);
+        else m_conv_s1_tile<T, NTC, true>(in, i0, q0, nt, bfr, bias, lane, epi);
+    }
+    if (NTC > 2 && q0 < nt) {  // ragged tail (NTC <= 2 is only chosen when it equals the n-tile count)
+        if (S2) m_conv_s2_tile<T, NTC, false>(in, i0, q0, nt, bfr, bias, lane, epi);
+        else m_conv_s1_tile<T, NTC, false>(in, i0, q0, nt, bfr, bias, lane, epi);
     }
 }
 
+template <typename T, bool S2, class Epi>
+__device__ __forceinline__ void m_conv_rows(const MBuf& in, int ntc, int i0, int nt, uint32_t bfr, float bias, int lane, Epi epi) {
+    if (ntc == 1) m_conv_chunks<T, S2, 1>(in, i0, nt, bfr, bias, lane, epi);
+    else if (ntc == 2) m_conv_chunks<T, S2, 2>(in, i0, nt, bfr, bias, lane, epi);
+    else if (S2 || ntc == 4) m_conv_chunks<T, S2, 4>(in, i0, nt, bfr, bias, lane, epi);  // `down`: at most 4 n-tiles per pass
+    else m_conv_chunks<T, S2, 7>(in, i0, nt, bfr, bias, lane, epi);
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// the kernel
+// team context
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 struct MTeam {
-    const MPlan& pl;
-    unsigned char* smem;
-    unsigned char* tsm;     // team slice
+    const MPlan& pl;   // layout (compile-time constants in the specialised kernels)
+    const MPlan& rt;   // run-time fields: B, C, n_cg, has_bias, wdtype, use_tma, dbg
+    uint32_t smem32, tsm32;   // shared addresses of the CTA's dynamic shared memory and of the team slice
     int team, wt, lane, tl;
     __device__ __forceinline__ void sync() const {
         if (pl.TW == 1) __syncwarp();
@@ -177,23 +194,23 @@ struct MTeam {
     __device__ __forceinline__ MBuf buf(int g, int l) const {
         MBuf b;
         const MLevel& lv = pl.lv[l];
-        b.base = rc_smem_u32(tsm + (long)g * pl.plane_bytes + lv.off);
+        b.base = l == 0 ? tsm32 + (uint32_t)(g * pl.l0_bytes) : tsm32 + (uint32_t)(pl.off_upper + g * pl.upper_bytes + lv.off);
         b.parDelta = (uint32_t)lv.parDelta;
         b.pitchB = lv.pitchB; b.H = lv.H; b.W = lv.W;
         return b;
     }
-    __device__ __forceinline__ uint32_t tbuf(int g) const { return rc_smem_u32(tsm + (long)g * pl.plane_bytes + pl.offT); }
-    __device__ __forceinline__ const uint32_t* frag(int g, int reg0) const {
-        return reinterpret_cast<const uint32_t*>(smem + pl.smFrag) + ((long)g * pl.nregs + reg0) * 32 + lane;
-    }
+    __device__ __forceinline__ uint32_t tbuf(int g) const { return tsm32 + (uint32_t)(pl.off_upper + g * pl.upper_bytes + pl.offT); }
+    __device__ __forceinline__ uint32_t frag(int g, int reg0) const { return smem32 + (uint32_t)(pl.smFrag + ((g * pl.nregs + reg0) * 32 + lane) * 4); }
     __device__ __forceinline__ float bias(int g, int slot) const {
-        return pl.has_bias ? reinterpret_cast<const float*>(smem + pl.smBias)[g * (pl.L + 2) + slot] : 0.f;
+        float v = 0.f;
+        if (rt.has_bias) asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(smem32 + (uint32_t)(pl.smBias + (g * (pl.L + 2) + slot) * 4)));
+        return v;
     }
 };
 
 // Toeplitz fragments + biases of channel group cg -> shared table (all threads of the CTA)
 template <typename T>
-__device__ __forceinline__ void m_build_frags(const MPlan& pl, const KernelArgs& a, unsigned char* smem, int cg, int tid, int nthreads) {
+__device__ __forceinline__ void m_build_frags(const MPlan& pl, const MPlan& rt, const KernelArgs& a, unsigned char* smem, int cg, int tid, int nthreads) {
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem + pl.smFrag);
     const int per = pl.nregs * 32;
     for (int idx = tid; idx < pl.G * per; idx += nthreads) {
@@ -208,7 +225,7 @@ __device__ __forceinline__ void m_build_frags(const MPlan& pl, const KernelArgs&
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int s = kbase + e - 2 * gq;
-                    if (s >= 0 && s <= 4) v[e] = rc_load_param(a.w[0], pl.wdtype, ch * 25 + r * 5 + s);
+                    if (s >= 0 && s <= 4) v[e] = rc_load_param(a.w[0], rt.wdtype, ch * 25 + r * 5 + s);
                 }
             }
         } else {
@@ -216,38 +233,47 @@ __device__ __forceinline__ void m_build_frags(const MPlan& pl, const KernelArgs&
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int s = kbase + e - gq;
-                if (s >= 0 && s <= 4) v[e] = rc_load_param(a.w[1 + j], pl.wdtype, ch * 25 + r * 5 + s);
+                if (s >= 0 && s <= 4) v[e] = rc_load_param(a.w[1 + j], rt.wdtype, ch * 25 + r * 5 + s);
             }
         }
         tab[idx] = MmaT<T>::pack(v[0], v[1]);
     }
-    if (pl.has_bias) {
+    if (rt.has_bias) {
         float* bt = reinterpret_cast<float*>(smem + pl.smBias);
         for (int idx = tid; idx < pl.G * (pl.L + 2); idx += nthreads) {
             const int p = idx / (pl.L + 2), slot = idx - p * (pl.L + 2);
             float v = 0.f;
-            if (a.b[slot] && !(slot == 0 && pl.L == 0)) v = rc_load_param(a.b[slot], pl.wdtype, (long)cg * pl.G + p);
+            if (a.b[slot] && !(slot == 0 && pl.L == 0)) v = rc_load_param(a.b[slot], rt.wdtype, (long)cg * pl.G + p);
             bt[idx] = v;
         }
     }
 }
 
-// raw planes (dense, element type T, generic address: shared after a bulk copy, else global) -> padded level 0
+// raw planes (dense, element type T, generic address: shared after a bulk copy, else global) -> padded level 0.
+// A lane owns column pair j of the rows i = rg, rg + RG, ...; the two row parities are walked separately so that
+// both the source and the destination address advance by a constant.
 template <typename T>
 __device__ __forceinline__ void m_repack(const MTeam<T>& tm, const T* __restrict__ src) {
     const MPlan& pl = tm.pl;
     const int H = pl.H, W = pl.W;
     const int LW = 1 << pl.rp_shift, RG = pl.team_lanes >> pl.rp_shift;
     const int j = tm.tl & (LW - 1), rg = tm.tl >> pl.rp_shift;
+    const MLevel& l0 = pl.lv[0];
     if ((W & 1) == 0) {
         const int CP = W >> 1;
         const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+        const uint32_t dstep = (uint32_t)(RG * l0.pitchB);
+        const int sstep = 2 * RG * CP;
         for (int g = 0; g < pl.G; ++g) {
             const MBuf b = tm.buf(g, 0);
-            for (int i = rg; i < H; i += RG) {
-                const uint32_t drow = b.row(i + 2) + 4u;
-                const uint32_t* srow = s32 + ((long)g * H + i) * CP;
-                for (int jj = j; jj < CP; jj += LW) m_sts32(drow + 4u * jj, srow[jj]);
+            for (int jj = j; jj < CP; jj += LW) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int i = rg + h * RG;
+                    uint32_t d = b.row(i + 2) + 4u + 4u * jj;
+                    const uint32_t* sp = s32 + (g * H + i) * CP + jj;
+                    for (; i < H; i += 2 * RG) { m_sts32(d, *sp); d += dstep; sp += sstep; }
+                }
             }
         }
     } else {
@@ -256,7 +282,7 @@ __device__ __forceinline__ void m_repack(const MTeam<T>& tm, const T* __restrict
             const MBuf b = tm.buf(g, 0);
             for (int i = rg; i < H; i += RG) {
                 const uint32_t drow = b.row(i + 2) + 4u;
-                const unsigned short* srow = s16 + ((long)g * H + i) * W;
+                const unsigned short* srow = s16 + (g * H + i) * W;
                 for (int jj = j; jj < W; jj += LW) m_sts16(drow + 2u * jj, srow[jj]);
             }
         }
@@ -265,12 +291,12 @@ __device__ __forceinline__ void m_repack(const MTeam<T>& tm, const T* __restrict
 
 // s_{l-1} = round(x_{l-1} + round(interpolate(t_l)))   (model/recnext.py:33 and the next `f + x`), table driven
 template <typename T>
-__device__ __forceinline__ void m_up_add(const MTeam<T>& tm, int l) {
+__device__ __forceinline__ void m_up_add(const MTeam<T>& tm, unsigned char* smem, int l) {
     const MPlan& pl = tm.pl;
     const MLevel& ls = pl.lv[l];
     const MLevel& ld = pl.lv[l - 1];
-    const IdxLam* ytab = reinterpret_cast<const IdxLam*>(tm.smem + pl.smTab + ls.tabY);
-    const IdxLam* xtab = reinterpret_cast<const IdxLam*>(tm.smem + pl.smTab + ls.tabX);
+    const IdxLam* ytab = reinterpret_cast<const IdxLam*>(smem + pl.smTab + ls.tabY);
+    const IdxLam* xtab = reinterpret_cast<const IdxLam*>(smem + pl.smTab + ls.tabX);
     const int LW = 1 << ls.up_shift, RG = pl.team_lanes >> ls.up_shift;
     const int j = tm.tl & (LW - 1), rg = tm.tl >> ls.up_shift;
     const int CP = (ld.W + 1) >> 1;
@@ -289,23 +315,22 @@ __device__ __forceinline__ void m_up_add(const MTeam<T>& tm, int l) {
             for (int i = rg; i < ld.H; i += RG) {
                 const IdxLam ty = ytab[i];
                 const uint32_t t0 = Tb + (uint32_t)ty.i0 * ls.tpB;
-                float u0, u1;
+                uint32_t u;
                 if (nearest) {
-                    const uint32_t w0 = m_lds16(t0 + xa0), w1 = m_lds16(t0 + xa1);
-                    u0 = MmaT<T>::unpack(w0).x; u1 = MmaT<T>::unpack(w1).x;
+                    u = m_lds16(t0 + xa0) | (v1 ? (m_lds16(t0 + xa1) << 16) : 0u);
                 } else {
                     const uint32_t t1 = t0 + ((ty.i0 < ls.H - 1) ? (uint32_t)ls.tpB : 0u);
                     const float ly = ty.lam, hy = 1.f - ly;
-                    const float a00 = MmaT<T>::unpack(m_lds16(t0 + xa0)).x, a01 = MmaT<T>::unpack(m_lds16(t0 + xb0)).x;
-                    const float a10 = MmaT<T>::unpack(m_lds16(t1 + xa0)).x, a11 = MmaT<T>::unpack(m_lds16(t1 + xb0)).x;
-                    const float b00 = MmaT<T>::unpack(m_lds16(t0 + xa1)).x, b01 = MmaT<T>::unpack(m_lds16(t0 + xb1)).x;
-                    const float b10 = MmaT<T>::unpack(m_lds16(t1 + xa1)).x, b11 = MmaT<T>::unpack(m_lds16(t1 + xb1)).x;
-                    u0 = MmaT<T>::rnd(hy * (hx0 * a00 + lx0 * a01) + ly * (hx0 * a10 + lx0 * a11));
-                    u1 = MmaT<T>::rnd(hy * (hx1 * b00 + lx1 * b01) + ly * (hx1 * b10 + lx1 * b11));
+                    const float a00 = MmaT<T>::one(m_lds16(t0 + xa0)), a01 = MmaT<T>::one(m_lds16(t0 + xb0));
+                    const float a10 = MmaT<T>::one(m_lds16(t1 + xa0)), a11 = MmaT<T>::one(m_lds16(t1 + xb0));
+                    const float b00 = MmaT<T>::one(m_lds16(t0 + xa1)), b01 = MmaT<T>::one(m_lds16(t0 + xb1));
+                    const float b10 = MmaT<T>::one(m_lds16(t1 + xa1)), b11 = MmaT<T>::one(m_lds16(t1 + xb1));
+                    const float u0 = hy * (hx0 * a00 + lx0 * a01) + ly * (hx0 * a10 + lx0 * a11);
+                    const float u1 = hy * (hx1 * b00 + lx1 * b01) + ly * (hx1 * b10 + lx1 * b11);
+                    u = MmaT<T>::pack(u0, v1 ? u1 : 0.f);
                 }
                 const uint32_t daddr = b.row(i + 2) + 4u + 4u * jj;
-                const float2 s = MmaT<T>::unpack(m_lds32(daddr));
-                m_sts32(daddr, MmaT<T>::pack(s.x + u0, v1 ? s.y + u1 : 0.f));
+                m_sts32(daddr, MmaT<T>::add2(m_lds32(daddr), u));
             }
         }
     }
@@ -313,52 +338,63 @@ __device__ __forceinline__ void m_up_add(const MTeam<T>& tm, int l) {
 
 // exact-2x bilinear (align_corners=False): fixed 0.75 / 0.25 stencil with the source index clamped at the borders
 // (ATen: even destination 2a -> sources a-1 (.25), a (.75); odd 2a+1 -> a (.75), a+1 (.25)).  A lane owns one column
-// pair (2a, 2a+1) of level l-1 = source columns a-1, a, a+1 (replicate border kept in T) and walks down source rows.
+// pair (2a, 2a+1) of level l-1 = source columns a-1, a, a+1 (replicate border kept in T) and walks down its block of
+// source rows; destination rows 2m and 2m+1 live in different parity arrays, each advancing by one pitch per source row.
 template <typename T>
 __device__ __forceinline__ void m_up2x_add(const MTeam<T>& tm, int l) {
     const MPlan& pl = tm.pl;
     const MLevel& ls = pl.lv[l];
-    const int LW = 1 << ls.up_shift, RG = pl.team_lanes >> ls.up_shift;
+    const int LW = 1 << ls.up_shift;
     const int j = tm.tl & (LW - 1), rg = tm.tl >> ls.up_shift;
     const int Hs = ls.H, Ws = ls.W;
-    const int rpg = (Hs + RG - 1) / RG;          // source rows per row group
+    const int rpg = ls.up_rpg;                    // source rows per row group
     const int m0 = rg * rpg, m1 = (m0 + rpg) < Hs ? (m0 + rpg) : Hs;
     if (m0 >= m1) return;
+    const uint32_t tpB = (uint32_t)ls.tpB;
     for (int a = j; a < Ws; a += LW) {
         for (int g = 0; g < pl.G; ++g) {
             const MBuf b = tm.buf(g, l - 1);
             const uint32_t Tc = tm.tbuf(g) + 2u * (a + 1);   // element a - 1 (interior at 2)
-            auto hrow = [&](int m, float& h0, float& h1) {
-                const uint32_t p = Tc + (uint32_t)m * ls.tpB;
-                const float ta = MmaT<T>::unpack(m_lds16(p)).x, tb = MmaT<T>::unpack(m_lds16(p + 2)).x, tc = MmaT<T>::unpack(m_lds16(p + 4)).x;
-                h0 = 0.25f * ta + 0.75f * tb;
-                h1 = 0.75f * tb + 0.25f * tc;
+            auto hrow = [&](uint32_t p, float& h0, float& h1) {
+                const float ta = MmaT<T>::one(m_lds16(p)), tb = MmaT<T>::one(m_lds16(p + 2)), tc = MmaT<T>::one(m_lds16(p + 4));
+                const float q = 0.75f * tb;
+                h0 = fmaf(0.25f, ta, q);
+                h1 = fmaf(0.25f, tc, q);
             };
             float p0, p1, c0, c1, n0, n1;
-            hrow(m0 > 0 ? m0 - 1 : 0, p0, p1);
-            hrow(m0, c0, c1);
+            hrow(Tc + (uint32_t)(m0 > 0 ? m0 - 1 : 0) * tpB, p0, p1);
+            uint32_t tp = Tc + (uint32_t)m0 * tpB;
+            hrow(tp, c0, c1);
+            uint32_t d0 = b.row(2 * m0 + 2) + 4u + 4u * a, d1 = b.row(2 * m0 + 3) + 4u + 4u * a;
             for (int m = m0; m < m1; ++m) {
-                hrow(m + 1 < Hs ? m + 1 : Hs - 1, n0, n1);
-                const uint32_t d0 = b.row(2 * m + 2) + 4u + 4u * a, d1 = b.row(2 * m + 3) + 4u + 4u * a;
-                const float2 s0 = MmaT<T>::unpack(m_lds32(d0)), s1 = MmaT<T>::unpack(m_lds32(d1));
-                const float e0 = MmaT<T>::rnd(0.25f * p0 + 0.75f * c0), e1 = MmaT<T>::rnd(0.25f * p1 + 0.75f * c1);
-                const float f0 = MmaT<T>::rnd(0.75f * c0 + 0.25f * n0), f1 = MmaT<T>::rnd(0.75f * c1 + 0.25f * n1);
-                m_sts32(d0, MmaT<T>::pack(s0.x + e0, s0.y + e1));
-                m_sts32(d1, MmaT<T>::pack(s1.x + f0, s1.y + f1));
+                if (m + 1 < Hs) tp += tpB;
+                hrow(tp, n0, n1);
+                const float q0 = 0.75f * c0, q1 = 0.75f * c1;
+                const uint32_t e = MmaT<T>::pack(fmaf(0.25f, p0, q0), fmaf(0.25f, p1, q1));
+                const uint32_t f = MmaT<T>::pack(fmaf(0.25f, n0, q0), fmaf(0.25f, n1, q1));
+                m_sts32(d0, MmaT<T>::add2(m_lds32(d0), e));
+                m_sts32(d1, MmaT<T>::add2(m_lds32(d1), f));
+                d0 += (uint32_t)b.pitchB; d1 += (uint32_t)b.pitchB;
                 p0 = c0; p1 = c1; c0 = n0; c1 = n1;
             }
         }
     }
 }
 
-// MAXT = 320: up to 10 warps with ~200 registers (wide planes: 7 n-tiles per pass); MAXT = 512: up to 16 warps at 128
-template <typename T, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) recconv_mfwd_kernel(const __grid_constant__ MPlan pl, const __grid_constant__ KernelArgs a) {
+// ---------------------------------------------------------------------------------------------------------
+// the kernel body.  pl = layout, rt = run-time fields (the same object in the generic kernel).  LS >= 0: the level
+// count is a compile-time constant and every loop over levels is fully unrolled, so that with a constexpr `pl`
+// all sizes, pitches and offsets become immediates.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int LS>
+__device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, const KernelArgs& a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int team = warp / pl.TW, wt = warp - team * pl.TW;
-    MTeam<T> tm{pl, smem, smem + pl.smTeams + (long)team * pl.team_bytes, team, wt, lane, wt * 32 + lane};
-    const int L = pl.L, G = pl.G;
+    const uint32_t smem32 = rc_smem_u32(smem);
+    MTeam<T> tm{pl, rt, smem32, smem32 + (uint32_t)(pl.smTeams + team * pl.team_bytes), team, wt, lane, wt * 32 + lane};
+    const int L = LS >= 0 ? LS : pl.L, G = pl.G;
+    const int lg = lane >> 2, lt = lane & 3;
 
     // ---- CTA init: zero the team slices (the borders of the padded buffers stay zero), interpolation tables, mbarriers
     {
@@ -366,128 +402,149 @@ __global__ void __launch_bounds__(MAXT, 1) recconv_mfwd_kernel(const __grid_cons
         const int n16 = pl.NTEAM * pl.team_bytes / 16;
         const uint4 zero = {0u, 0u, 0u, 0u};
         for (int i = tid; i < n16; i += blockDim.x) z[i] = zero;
+#pragma unroll
         for (int l = 1; l <= L; ++l) {
             rc_build_fwd_table(reinterpret_cast<IdxLam*>(smem + pl.smTab + pl.lv[l].tabY), pl.lv[l].H, pl.lv[l - 1].H, pl.mode, tid, blockDim.x);
             rc_build_fwd_table(reinterpret_cast<IdxLam*>(smem + pl.smTab + pl.lv[l].tabX), pl.lv[l].W, pl.lv[l - 1].W, pl.mode, tid, blockDim.x);
         }
     }
-    const uint32_t bar = rc_smem_u32(smem + pl.smBar + 8 * team);
+    const uint32_t bar = smem32 + (uint32_t)(pl.smBar + 8 * team);
     uint32_t phase = 0;
-    if (pl.use_tma && tm.tl == 0) rc_mbar_init(bar, 1);
+    if (rt.use_tma && tm.tl == 0) rc_mbar_init(bar, 1);
     rc_fence_proxy_async();  // the zero fill above also touched the bulk-copy buffers
     __syncthreads();
 
-    const long plane_elems = (long)pl.H * pl.W;
+    const int plane_elems = pl.H * pl.W;
     const T* gx = reinterpret_cast<const T*>(a.x);
     T* gy = reinterpret_cast<T*>(a.out);
-    const long total = (long)pl.n_cg * pl.B;
+    const long total = (long)rt.n_cg * rt.B;
     const long start = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
     if (start >= end) return;
     long my = start + team;
-    unsigned char* raw = tm.tsm + pl.off_raw;
-    auto plane0_of = [&](long idx) { const long cg = idx / pl.B, n = idx - cg * pl.B; return (n * pl.C + cg * G) * plane_elems; };
-    if (pl.use_tma && my < end && tm.tl == 0) {
-        rc_mbar_expect_tx(bar, (uint32_t)pl.raw_bytes);
-        rc_bulk_g2s(raw, gx + plane0_of(my), (uint32_t)pl.raw_bytes, bar);
-    }
-    const int cg_first = (int)(start / pl.B), cg_last = (int)((end - 1) / pl.B);
+    unsigned char* raw = smem + pl.smTeams + team * pl.team_bytes + pl.off_upper;   // aliases levels >= 1 and T
+    auto plane0_of = [&](long idx) { const int cg = (int)(idx / rt.B), n = (int)(idx - (long)cg * rt.B); return ((long)n * rt.C + cg * G) * (long)plane_elems; };
+    auto issue_load = [&](long idx) {
+        if (tm.tl == 0) {
+            rc_mbar_expect_tx(bar, (uint32_t)pl.raw_bytes);
+            rc_bulk_g2s(raw, gx + plane0_of(idx), (uint32_t)pl.raw_bytes, bar);
+        }
+    };
+    if (rt.use_tma && my < end) issue_load(my);
+    const int cg_first = (int)(start / rt.B), cg_last = (int)((end - 1) / rt.B);
     for (int cg = cg_first; cg <= cg_last; ++cg) {
         __syncthreads();  // every team is done with the previous channel group's fragments
-        m_build_frags<T>(pl, a, smem, cg, tid, blockDim.x);
+        m_build_frags<T>(pl, rt, a, smem, cg, tid, blockDim.x);
         __syncthreads();
-        const long cg_end = ((long)(cg + 1) * pl.B) < end ? ((long)(cg + 1) * pl.B) : end;
+        const long cg_end = ((long)(cg + 1) * rt.B) < end ? ((long)(cg + 1) * rt.B) : end;
         for (; my < cg_end; my += pl.NTEAM) {
             const long p0 = plane0_of(my);
+            const long nxt = my + pl.NTEAM;
             // ---- x -> padded level 0
-            if (pl.use_tma) {
+            if (rt.use_tma) {
                 while (!rc_mbar_try_wait(bar, phase)) {}
                 phase ^= 1u;
                 m_repack<T>(tm, reinterpret_cast<const T*>(raw));
-                rc_fence_proxy_async();  // order these generic reads of `raw` before the next bulk copy's writes
                 tm.sync();
-                const long nxt = my + pl.NTEAM;
-                if (nxt < end && tm.tl == 0) {
-                    rc_mbar_expect_tx(bar, (uint32_t)pl.raw_bytes);
-                    rc_bulk_g2s(raw, gx + plane0_of(nxt), (uint32_t)pl.raw_bytes, bar);
+                if (L == 0) {
+                    rc_fence_proxy_async();  // generic reads of `raw` before the next bulk copy's writes
+                    if (nxt < end) issue_load(nxt);
+                } else {
+                    // the raw batch landed on top of levels >= 1: restore their zero borders
+                    const uint4 zero = {0u, 0u, 0u, 0u};
+                    for (int g = 0; g < G; ++g) {
+                        uint4* z = reinterpret_cast<uint4*>(raw + g * pl.upper_bytes);
+                        for (int i = tm.tl; i < pl.zero_bytes / 16; i += pl.team_lanes) z[i] = zero;
+                    }
+                    tm.sync();
                 }
             } else {
                 m_repack<T>(tm, gx + p0);
                 tm.sync();
             }
             // ---- down chain: x_l = down(x_{l-1})   (model/recnext.py:27-29)
+#pragma unroll
             for (int l = 1; l <= L; ++l) {
                 const MLevel& lo = pl.lv[l];
-                for (int it = wt; it < G * lo.MT; it += pl.TW) {
-                    const int g = it / lo.MT, mt = it - g * lo.MT;
+                for (int g = 0, mt = wt; g < G; mt += pl.TW) {
+                    if (mt >= lo.MT) { mt -= lo.MT + pl.TW; ++g; continue; }
                     const MBuf in = tm.buf(g, l - 1);
                     const MBuf out = tm.buf(g, l);
-                    const int i0 = mt * 16, Ho = lo.H, Wo = lo.W;
+                    const int i0 = mt * 16, Wo = lo.W;
+                    const int ia = i0 + lg, ib = ia + 8;
+                    const bool va = ia < lo.H, vb = ib < lo.H;
+                    const uint32_t da = out.row(ia + 2) + 4u + 4u * lt, db = out.row(ib + 2) + 4u + 4u * lt;
                     m_conv_rows<T, true>(in, lo.ntc, i0, lo.NT, tm.frag(g, 0), tm.bias(g, 0), lane, [&](int q, const float (&acc)[4]) {
-                        const int c = 8 * q + 2 * (lane & 3);
+                        const int c = 8 * q + 2 * lt;
                         if (c < Wo) {
                             const bool pair = c + 1 < Wo;
-                            const int ia = i0 + (lane >> 2), ib = ia + 8;
-                            if (ia < Ho) m_sts32(out.row(ia + 2) + 4u + 2u * c, MmaT<T>::pack(acc[0], pair ? acc[1] : 0.f));
-                            if (ib < Ho) m_sts32(out.row(ib + 2) + 4u + 2u * c, MmaT<T>::pack(acc[2], pair ? acc[3] : 0.f));
+                            if (va) m_sts32(da + 16u * q, MmaT<T>::pack(acc[0], pair ? acc[1] : 0.f));
+                            if (vb) m_sts32(db + 16u * q, MmaT<T>::pack(acc[2], pair ? acc[3] : 0.f));
                         }
                     });
                 }
                 tm.sync();
             }
             // ---- up pass: t_l = convs[L-l](s_l); s_{l-1} = x_{l-1} + interpolate(t_l)   (model/recnext.py:31-33)
+#pragma unroll
             for (int l = L; l >= 1; --l) {
                 const MLevel& lv = pl.lv[l];
-                for (int it = wt; it < G * lv.MT; it += pl.TW) {
-                    const int g = it / lv.MT, mt = it - g * lv.MT;
+                for (int g = 0, mt = wt; g < G; mt += pl.TW) {
+                    if (mt >= lv.MT) { mt -= lv.MT + pl.TW; ++g; continue; }
                     const MBuf in = tm.buf(g, l);
-                    const uint32_t Tb = tm.tbuf(g);
-                    const int i0 = mt * 16, Hl = lv.H, Wl = lv.W, tpB = lv.tpB;
+                    const int i0 = mt * 16, Wl = lv.W;
+                    const int ia = i0 + 2 * lg;
+                    const bool va = ia < lv.H, vb = ia + 1 < lv.H;
+                    const uint32_t ta = tm.tbuf(g) + (uint32_t)(ia * lv.tpB) + 4u + 4u * lt, tpB = (uint32_t)lv.tpB;
                     m_conv_rows<T, false>(in, lv.ntc, i0, lv.NT, tm.frag(g, 20 + 10 * (L - l)), tm.bias(g, 1 + (L - l)), lane,
                                           [&](int q, const float (&acc)[4]) {
-                        const int c = 8 * q + 2 * (lane & 3);
+                        const int c = 8 * q + 2 * lt;
                         if (c < Wl) {
-                            const int ia = i0 + 2 * (lane >> 2);
+                            const bool pair = c + 1 < Wl;  // else column c is the last one: its pair slot is the replicate border
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
-                                const int i = ia + h;
-                                if (i < Hl) {
-                                    const float lo = acc[2 * h], hi = (c + 1 < Wl) ? acc[2 * h + 1] : acc[2 * h];
-                                    const uint32_t w = MmaT<T>::pack(lo, hi);
-                                    const uint32_t ad = Tb + (uint32_t)i * tpB + 2u * (c + 2);
-                                    m_sts32(ad, w);                                          // (c == W-1: the pair's high half is the replicate border)
-                                    if (c == 0) m_sts16(ad - 2u, w & 0xffffu);                // left replicate border
-                                    if (c + 1 == Wl - 1) m_sts16(ad + 4u, w >> 16);           // right replicate border
+                                if (h ? vb : va) {
+                                    const uint32_t w = MmaT<T>::pack(acc[2 * h], pair ? acc[2 * h + 1] : acc[2 * h]);
+                                    const uint32_t ad = ta + h * tpB + 16u * q;
+                                    m_sts32(ad, w);
+                                    if (c == 0) m_sts16(ad - 2u, w);                       // left replicate border
+                                    if (c + 1 == Wl - 1) m_sts16(ad + 4u, w >> 16);        // right replicate border
                                 }
                             }
                         }
                     });
                 }
                 tm.sync();
-                if (lv.exact2x && pl.mode == 0 && !(pl.dbg & 1)) m_up2x_add<T>(tm, l);
-                else m_up_add<T>(tm, l);
+                if (lv.exact2x && pl.mode == 0 && !(rt.dbg & 1)) m_up2x_add<T>(tm, l);
+                else m_up_add<T>(tm, smem, l);
                 tm.sync();
+            }
+            if (rt.use_tma && L > 0) {  // levels >= 1 and T are dead: fetch the next batch under the final conv
+                rc_fence_proxy_async();
+                tm.sync();
+                if (nxt < end) issue_load(nxt);
             }
             // ---- y = convs[L](s_0) -> global   (model/recnext.py:34)
             {
                 const MLevel& lv = pl.lv[0];
                 const int H = pl.H, W = pl.W;
-                for (int it = wt; it < G * lv.MT; it += pl.TW) {
-                    const int g = it / lv.MT, mt = it - g * lv.MT;
+                for (int g = 0, mt = wt; g < G; mt += pl.TW) {
+                    if (mt >= lv.MT) { mt -= lv.MT + pl.TW; ++g; continue; }
                     const MBuf in = tm.buf(g, 0);
-                    T* dst = gy + p0 + (long)g * plane_elems;
                     const int i0 = mt * 16;
+                    const int ia = i0 + 2 * lg;
+                    const bool va = ia < H, vb = ia + 1 < H;
+                    T* da = gy + p0 + (long)g * plane_elems + ia * W + 2 * lt;
+                    const bool even = (W & 1) == 0;
                     m_conv_rows<T, false>(in, lv.ntc, i0, lv.NT, tm.frag(g, 20 + 10 * L), tm.bias(g, 1 + L), lane,
                                           [&](int q, const float (&acc)[4]) {
-                        const int c = 8 * q + 2 * (lane & 3);
+                        const int c = 8 * q + 2 * lt;
                         if (c < W) {
-                            const int ia = i0 + 2 * (lane >> 2);
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
-                                const int i = ia + h;
-                                if (i < H) {
+                                if (h ? vb : va) {
                                     const uint32_t w = MmaT<T>::pack(acc[2 * h], acc[2 * h + 1]);
-                                    T* d = dst + (long)i * W + c;
-                                    if ((W & 1) == 0) *reinterpret_cast<uint32_t*>(d) = w;
+                                    T* d = da + h * W + 8 * q;
+                                    if (even) *reinterpret_cast<uint32_t*>(d) = w;
                                     else {
                                         *reinterpret_cast<unsigned short*>(d) = (unsigned short)(w & 0xffffu);
                                         if (c + 1 < W) *reinterpret_cast<unsigned short*>(d + 1) = (unsigned short)(w >> 16);
@@ -503,24 +560,59 @@ __global__ void __launch_bounds__(MAXT, 1) recconv_mfwd_kernel(const __grid_cons
     }
 }
 
+// generic kernel: everything from the run-time plan.  Up to 16 warps at 128 registers.
 template <typename T>
-inline cudaError_t m_launch_fwd_t(const MPlan& pl, const KernelArgs& a, cudaStream_t stream) {
+__global__ void __launch_bounds__(512, 1) recconv_mfwd_kernel(const __grid_constant__ MPlan pl, const __grid_constant__ KernelArgs a) {
+    m_fwd_body<T, -1>(pl, pl, a);
+}
+// specialised kernel: plane geometry (H0 x W0, L0 levels, G0 planes per batch) fixed at compile time
+template <typename T, int H0, int W0, int L0, int G0>
+__global__ void __launch_bounds__(512, 1) recconv_mfwd_static_kernel(const __grid_constant__ MPlan rt, const __grid_constant__ KernelArgs a) {
+    constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1);
+    m_fwd_body<T, L0>(sp, rt, a);
+}
+
+template <typename T, int H0, int W0, int L0, int G0>
+inline bool m_try_static(const MPlan& pl, const KernelArgs& a, cudaStream_t stream, cudaError_t& err) {
+    constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1);
+    if (pl.H != H0 || pl.W != W0 || pl.L != L0 || pl.G != G0) return false;
+    const MPlan st = m_static_patched(sp, pl);
+    if (memcmp(&st, &pl, sizeof(MPlan)) != 0) return false;
     static int configured = 0;  // benign race: idempotent
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(recconv_mfwd_kernel<T, 320>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(recconv_mfwd_kernel<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
+        err = cudaFuncSetAttribute(recconv_mfwd_static_kernel<T, H0, W0, L0, G0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err != cudaSuccess) return true;
         configured = 1;
     }
-    if (pl.threads <= 320) recconv_mfwd_kernel<T, 320><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
-    else recconv_mfwd_kernel<T, 512><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
+    recconv_mfwd_static_kernel<T, H0, W0, L0, G0><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
+    err = cudaGetLastError();
+    return true;
+}
+
+template <typename T>
+inline cudaError_t m_launch_fwd_t(const MPlan& pl, const KernelArgs& a, cudaStream_t stream, bool allow_static) {
+    cudaError_t err = cudaSuccess;
+    // the RecNeXt stage shapes at 224 px (model/recnext.py:152: level = 4 - stage)
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) if (allow_static) {
+        if (m_try_static<T, 56, 56, 4, 1>(pl, a, stream, err)) return err;
+        if (m_try_static<T, 28, 28, 3, 1>(pl, a, stream, err)) return err;
+        if (m_try_static<T, 14, 14, 2, 4>(pl, a, stream, err)) return err;
+        if (m_try_static<T, 7, 7, 1, 8>(pl, a, stream, err)) return err;
+    }
+    static int configured = 0;  // benign race: idempotent
+    if (!configured) {
+        err = cudaFuncSetAttribute(recconv_mfwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err != cudaSuccess) return err;
+        configured = 1;
+    }
+    recconv_mfwd_kernel<T><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
     return cudaGetLastError();
 }
 
 inline cudaError_t m_launch_fwd(const MPlan& pl, const KernelArgs& a, cudaStream_t stream) {
-    if (pl.dtype == 1) return m_launch_fwd_t<__nv_bfloat16>(pl, a, stream);
-    if (pl.dtype == 2) return m_launch_fwd_t<__half>(pl, a, stream);
+    const bool allow_static = !(pl.dbg & 2);
+    if (pl.dtype == 1) return m_launch_fwd_t<__nv_bfloat16>(pl, a, stream, allow_static);
+    if (pl.dtype == 2) return m_launch_fwd_t<__half>(pl, a, stream, allow_static);
     return cudaErrorInvalidValue;
 }
 

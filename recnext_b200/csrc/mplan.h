@@ -34,6 +34,7 @@ struct MLevel {
     int tabY, tabX;      // l >= 1: byte offsets (table region) of IdxLam[H_{l-1}] / IdxLam[W_{l-1}]
     int exact2x;         // level l-1 is exactly 2x this level
     int up_shift;        // l >= 1: up-add lane mapping over level l-1: lanes per row group = 1 << up_shift
+    int up_rpg;          // l >= 1: exact-2x path: source rows per row group
 };
 
 struct MPlan {
@@ -43,10 +44,15 @@ struct MPlan {
     int use_tma;
     int rp_shift;        // repack lane mapping (column pairs of level 0, or columns if W is odd)
     MLevel lv[kMaxLevel + 1];
-    int plane_bytes;     // one plane block: all level buffers + T
-    int offT;            // byte offset of the T buffer inside a plane block
+    int l0_bytes;        // level-0 buffer of one plane (the team slice starts with G of them)
+    int upper_bytes;     // levels 1..L + T of one plane (MLevel::off of l >= 1 and offT are relative to this block)
+    int zero_bytes;      // leading part of an upper block that holds padded level buffers (re-zeroed per batch when the
+                         // raw batch aliases the upper region)
+    int offT;            // byte offset of the T buffer inside an upper block
     int raw_bytes;       // G raw planes
-    int off_raw, team_bytes;
+    int off_upper;       // byte offset (team slice) of the upper region = the TMA landing buffer: a batch is loaded
+                         // only after the last use of levels >= 1 and T (under the final conv)
+    int team_bytes;
     int nregs;           // Toeplitz fragment registers per channel: 20 (down) + 10 per conv
     int smBar, smTab, smFrag, smBias, smTeams, smem_bytes;
     int grid;
@@ -59,16 +65,22 @@ struct MPlanOptions {
     int smem_limit = 227 * 1024;
 };
 
-RC_H int m_pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
-RC_H int m_log2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+RC_HD constexpr int m_pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+RC_HD constexpr int m_log2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+RC_HD constexpr int m_lane_shift(int pairs, int team_lanes) {
+    int p = m_pow2_ceil(pairs);
+    if (p > team_lanes) p = team_lanes;
+    return m_log2(p);
+}
 
 // 0 ok; 1 not eligible / does not fit (caller uses the FMA kernels); 2 bad arguments
-RC_H int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mode, int dtype, int wdtype, int has_bias,
+RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mode, int dtype, int wdtype, int has_bias,
                      const MPlanOptions& opt) {
     if (B < 1 || C < 1 || H < 1 || W < 1 || L < 0 || L > kMaxLevel) return 2;
     if (K != 5 || !(dtype == 1 || dtype == 2)) return 1;
     if (H > 1023 || W > 1023) return 1;
-    pl = MPlan();
+    pl = MPlan{};
     pl.B = B; pl.C = C; pl.H = H; pl.W = W; pl.L = L; pl.mode = mode; pl.dtype = dtype; pl.wdtype = wdtype; pl.has_bias = has_bias;
     pl.dbg = opt.dbg;
     pl.lv[0].H = H; pl.lv[0].W = W;
@@ -78,13 +90,12 @@ RC_H int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mo
         g.NT = rc_div_up(g.W, 8); g.MT = rc_div_up(g.H, 16);
         g.ntc = g.NT <= 1 ? 1 : (g.NT == 2 ? 2 : (g.NT <= 4 ? 4 : 7));
     }
-    // level buffers
+    // level buffers: level 0 on its own, levels >= 1 + T in the "upper" block
     int off = 0, tmax = 0;
     for (int l = 0; l <= L; ++l) {
         MLevel& g = pl.lv[l];
         int kb = g.NT + 1;                                        // as the input of a stride-1 conv
         if (l < L && 2 * pl.lv[l + 1].NT + 1 > kb) kb = 2 * pl.lv[l + 1].NT + 1;  // as the input of `down`
-        if ((g.W + 4 + 7) / 8 > kb) kb = (g.W + 4 + 7) / 8;
         if ((kb & 1) == 0) ++kb;
         g.pitchB = 16 * kb;
         const int rows = g.H + 4, nE = (rows + 1) / 2, nO = rows / 2;
@@ -94,15 +105,17 @@ RC_H int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mo
         g.parDelta = d;
         off += d + nO * g.pitchB + 16;
         off = rc_round_up(off, 128);
+        if (l == 0) { pl.l0_bytes = off; off = 0; }
         g.exact2x = (l >= 1 && pl.lv[l - 1].H == 2 * g.H && pl.lv[l - 1].W == 2 * g.W) ? 1 : 0;
         if (l >= 1) {
             g.tpB = rc_round_up((g.W + 4) * 2, 4);
             if (g.H * g.tpB > tmax) tmax = g.H * g.tpB;
         }
     }
+    pl.zero_bytes = off;
     pl.offT = off;
     off += rc_round_up(tmax, 128);
-    pl.plane_bytes = off;
+    pl.upper_bytes = off;
 
     // tables shared by the CTA
     int tb = 0;
@@ -127,8 +140,12 @@ RC_H int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mo
     pl.use_tma = (!opt.force_no_tma && (pl.raw_bytes % 16) == 0 && pl.raw_bytes <= 64 * 1024) ? 1 : 0;
     pl.nregs = 20 + 10 * (L + 1);
 
-    pl.off_raw = G * pl.plane_bytes;
-    pl.team_bytes = pl.off_raw + (pl.use_tma ? rc_round_up(pl.raw_bytes, 128) : 0);
+    pl.off_upper = G * pl.l0_bytes;
+    {
+        int up = G * pl.upper_bytes;
+        if (pl.use_tma && rc_round_up(pl.raw_bytes, 128) > up) up = rc_round_up(pl.raw_bytes, 128);
+        pl.team_bytes = pl.off_upper + up;
+    }
     pl.smBar = 0;
     pl.smTab = 256;
     pl.smFrag = pl.smTab + tb;
@@ -152,9 +169,11 @@ RC_H int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mo
     if (pl.smem_bytes > opt.smem_limit) return 1;
 
     // lane mappings of the element-wise stages: (row group, column pair)
-    auto shift_for = [&](int pairs) { int p = m_pow2_ceil(pairs); if (p > pl.team_lanes) p = pl.team_lanes; return m_log2(p); };
-    pl.rp_shift = shift_for((W & 1) ? W : W / 2);
-    for (int l = 1; l <= L; ++l) pl.lv[l].up_shift = shift_for((pl.lv[l - 1].W + 1) / 2);
+    pl.rp_shift = m_lane_shift((W & 1) ? W : W / 2, pl.team_lanes);
+    for (int l = 1; l <= L; ++l) {
+        pl.lv[l].up_shift = m_lane_shift((pl.lv[l - 1].W + 1) / 2, pl.team_lanes);
+        pl.lv[l].up_rpg = rc_div_up(pl.lv[l].H, pl.team_lanes >> pl.lv[l].up_shift);
+    }
 
     const long total = (long)pl.n_cg * B;
     long grid = opt.num_sms;
@@ -162,6 +181,24 @@ RC_H int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, int L, int mo
     if (grid < 1) grid = 1;
     pl.grid = (int)grid;
     return 0;
+}
+
+// The layout-defining part of a plan for fixed plane geometry, evaluated at COMPILE time by the specialised kernels
+// (mfwd.cuh): every level size, pitch and offset folds into immediates.  The host compares it field by field with
+// the run-time plan before choosing a specialised kernel; B, C, grid, bias, parameter dtype and TMA eligibility
+// stay run-time values.
+RC_HD constexpr MPlan m_static_plan(int H, int W, int L, int G, int dtype) {
+    MPlan pl{};
+    MPlanOptions o{};
+    o.force_G = G;
+    m_make_plan(pl, 1, G, H, W, 5, L, 0, dtype, dtype, 0, o);
+    return pl;
+}
+// copies the run-time fields of `rt` into a static plan so that the two can be compared with memcmp
+RC_H MPlan m_static_patched(MPlan st, const MPlan& rt) {
+    st.B = rt.B; st.C = rt.C; st.n_cg = rt.n_cg; st.has_bias = rt.has_bias; st.wdtype = rt.wdtype; st.use_tma = rt.use_tma;
+    st.grid = rt.grid; st.dbg = rt.dbg;
+    return st;
 }
 
 }  // namespace recnext

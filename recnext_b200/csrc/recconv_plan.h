@@ -98,9 +98,9 @@ struct GatherEntry {  // bwd: the (<= 4) destinations d0..d0+n-1 of level l-1 th
     int pad_[2];
 };
 
-RC_HD int rc_down_size(int n, int k) { return (n + 2 * (k / 2) - k) / 2 + 1; }
-RC_HD int rc_round_up(int v, int m) { return (v + m - 1) / m * m; }
-RC_HD int rc_div_up(int a, int b) { return (a + b - 1) / b; }
+RC_HD constexpr int rc_down_size(int n, int k) { return (n + 2 * (k / 2) - k) / 2 + 1; }
+RC_HD constexpr int rc_round_up(int v, int m) { return (v + m - 1) / m * m; }
+RC_HD constexpr int rc_div_up(int a, int b) { return (a + b - 1) / b; }
 // x / n for 0 <= x < 2^16 by multiplication: magic = floor(2^32 / n) + 1 (n >= 2); magic 0 encodes n == 1
 RC_HD unsigned rc_magic(int n) { return n <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned long long)n) + 1u; }
 RC_HD int rc_fastdiv(int x, unsigned magic) {
