@@ -91,6 +91,23 @@ RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d);
 RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx,
                      float* gw, float* gb, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * RecAttn2d (A-series token mixer, reference model/recattn.py:54-67), the two plane-independent pieces around the
+ * linear attention, for 16-bit activations (bf16 / fp16; k = 5; BatchNorm folded into w, b as ConvNorm.fuse does,
+ * model/recattn.py:87-111).  Inference entry points: there is no backward for them yet.
+ *
+ *   recattn_down_forward  replaces  RecAttn2d.down[0]                      model/recattn.py:60,67
+ *       out[B,C,H1,W1] = depthwise k x k stride-2 conv of x[B,C,H,W] (+ b),  H1 = (H-1)/2+1, W1 = (W-1)/2+1
+ *   recattn_up_forward    replaces  self.conv(x + F.interpolate(z, size=x.shape[2:], mode))   model/recattn.py:67
+ *       y[B,C,H,W] = depthwise k x k conv of (x + interpolate(z[B,C,zH,zW])) (+ b)
+ *
+ * d->level is ignored; d->mode selects the interpolation of recattn_up_forward (the reference default is nearest).
+ * w: [C,1,k,k], b: [C] or NULL (must be non-NULL iff d->has_bias), dtype d->wdtype.
+ */
+RECNEXT_API int recattn_down_forward(const recconv_desc* d, const void* w, const void* b, const void* x, void* out, void* stream);
+RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const void* b, const void* x, const void* z, int32_t zH,
+                                   int32_t zW, void* y, void* stream);
+
 /* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);
 

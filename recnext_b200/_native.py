@@ -64,6 +64,12 @@ def lib() -> ctypes.CDLL:
     L.recconv_plan_describe.argtypes = [ctypes.POINTER(RecConvDesc), ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
     L.recconv_source_index.restype = ctypes.c_int
     L.recconv_source_index.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.recattn_down_forward.restype = ctypes.c_int
+    L.recattn_down_forward.argtypes = [ctypes.POINTER(RecConvDesc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]
+    L.recattn_up_forward.restype = ctypes.c_int
+    L.recattn_up_forward.argtypes = [ctypes.POINTER(RecConvDesc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     _lib = L
     return L
 
@@ -76,5 +82,5 @@ def check(rc: int, what: str) -> None:
 
 EXPORTS = [
     "recnext_abi_version", "recnext_last_error", "recconv_forward", "recconv_backward_workspace_bytes", "recconv_backward",
-    "recconv_plan_describe", "recconv_source_index",
+    "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward",
 ]

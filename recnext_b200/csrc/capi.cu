@@ -14,6 +14,7 @@
 
 namespace recnext {
 cudaError_t m_launch(const MPlan&, const KernelArgs&, cudaStream_t);  // recconv_m5.cu: tensor-core forward
+bool m_static_geometry(const MPlan&);
 template <int K, typename T, bool BWD> cudaError_t w_launch(const WPlan&, const KernelArgs&, cudaStream_t);
 typedef cudaError_t (*w_launch_fn)(const WPlan&, const KernelArgs&, cudaStream_t);
 #define W_DECLARE_K(K)                                                                                           \
@@ -159,15 +160,9 @@ static bool fma_forced() {
     if (v < 0) { const char* e = getenv("RECNEXT_PATH"); v = (e && (strcmp(e, "fma") == 0 || strcmp(e, "legacy") == 0)) ? 1 : 0; }
     return v == 1;
 }
-// while the tensor-core forward is being tuned it is opt-in: RECNEXT_PATH=mma
-static bool mma_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("RECNEXT_PATH"); v = (e && strcmp(e, "mma") == 0) ? 1 : 0; }
-    return v == 1;
-}
 // 0: tensor-core forward plan made (16-bit activations, k = 5); 1: not eligible
 static int make_mplan(const recconv_desc* d, MPlan& pl) {
-    if (fma_forced() || !mma_enabled() || d->k != 5 || !(d->dtype == RECNEXT_BF16 || d->dtype == RECNEXT_F16)) return 1;
+    if (fma_forced() || d->k != 5 || !(d->dtype == RECNEXT_BF16 || d->dtype == RECNEXT_F16)) return 1;
     MPlanOptions opt;
     opt.num_sms = device_sms();
     if (const char* e = getenv("RECNEXT_MG")) opt.force_G = atoi(e);
@@ -175,6 +170,11 @@ static int make_mplan(const recconv_desc* d, MPlan& pl) {
     if (const char* e = getenv("RECNEXT_MNT")) opt.force_NT = atoi(e);
     if (const char* e = getenv("RECNEXT_MNOTMA")) opt.force_no_tma = atoi(e);
     if (const char* e = getenv("RECNEXT_MDBG")) opt.dbg = atoi(e);
+    // planes smaller than one 16x8 MMA tile waste most of the tensor work: the FMA kernels are faster there
+    // (measured, [256,512,7,7] L1 bf16: 0.098 ms FMA vs 0.118 ms MMA); RECNEXT_PATH=mma overrides for experiments
+    static int force_mma = -1;
+    if (force_mma < 0) { const char* e = getenv("RECNEXT_PATH"); force_mma = (e && strcmp(e, "mma") == 0) ? 1 : 0; }
+    if (!force_mma && d->H * d->W < 100) return 1;
     return m_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, opt) == 0 ? 0 : 1;
 }
 
@@ -243,6 +243,44 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
     const cudaError_t e = fn(pl, a, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward: %s", cudaGetErrorString(e));
     return RECNEXT_OK;
+}
+
+// RecAttn2d pieces: variants 1 / 2 of the tensor-core forward kernel
+static int recattn_launch(const recconv_desc* d, int variant, const void* w, const void* b, const void* x, const void* z, int zH, int zW,
+                          void* out, void* stream, const char* what) {
+    if (int rc = check_desc(d)) return rc;
+    if (d->B == 0 || d->C == 0) return RECNEXT_OK;
+    if (!x || !out || !w || (variant == 2 && !z)) return fail(RECNEXT_EINVAL, "%s: null tensor", what);
+    if ((d->has_bias != 0) != (b != nullptr)) return fail(RECNEXT_EINVAL, "%s: b must be given iff has_bias", what);
+    if (d->k != 5 || !(d->dtype == RECNEXT_BF16 || d->dtype == RECNEXT_F16))
+        return fail(RECNEXT_EUNSUPPORTED, "%s: built for 16-bit activations and kernel_size 5 (tensor-core path) only", what);
+    if ((((uintptr_t)x | (uintptr_t)out | (uintptr_t)z) & 3) != 0) return fail(RECNEXT_EINVAL, "%s: tensors must be 4-byte aligned", what);
+    MPlanOptions opt;
+    opt.num_sms = device_sms();
+    opt.variant = variant; opt.zH = zH; opt.zW = zW;
+    if (const char* e = getenv("RECNEXT_MDBG")) opt.dbg = atoi(e);
+    MPlan mp;
+    const int rc = m_make_plan(mp, d->B, d->C, d->H, d->W, d->k, 1, d->mode, d->dtype, d->wdtype, d->has_bias, opt);
+    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "%s: a %dx%d plane does not fit in 227 KB of shared memory", what, d->H, d->W);
+    if (rc) return fail(RECNEXT_EINVAL, "%s: bad arguments", what);
+    if (((uintptr_t)x & 15) != 0) mp.use_tma = 0;
+    KernelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.gy = z; a.out = out;
+    if (variant == 1) { a.w[0] = w; a.b[0] = b; }
+    else { a.w[2] = w; a.b[2] = b; }   // slot of convs[L] with L = 1
+    const cudaError_t e = m_launch(mp, a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    return RECNEXT_OK;
+}
+
+RECNEXT_API int recattn_down_forward(const recconv_desc* d, const void* w, const void* b, const void* x, void* out, void* stream) {
+    return recattn_launch(d, 1, w, b, x, nullptr, 0, 0, out, stream, "recattn_down_forward");
+}
+RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const void* b, const void* x, const void* z, int32_t zH, int32_t zW,
+                       void* y, void* stream) {
+    if (zH < 1 || zW < 1) return fail(RECNEXT_EINVAL, "recattn_up_forward: bad z size %dx%d", zH, zW);
+    return recattn_launch(d, 2, w, b, x, z, zH, zW, y, stream, "recattn_up_forward");
 }
 
 RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
@@ -316,9 +354,9 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
     if (!backward && make_mplan(d, mp) == 0) {
         snprintf(buf, buflen,
                  "fwd tensor-core k=5 L=%d [%d,%d,%d,%d] planes/batch=%d warps/team=%d teams/CTA=%d threads=%d grid=%d smem=%d B team=%d B "
-                 "plane=%d B frag-regs/channel=%d tma=%d",
+                 "plane=%d B frag-regs/channel=%d tma=%d geometry=%s",
                  mp.L, mp.B, mp.C, mp.H, mp.W, mp.G, mp.TW, mp.NTEAM, mp.threads, mp.grid, mp.smem_bytes, mp.team_bytes, mp.l0_bytes + mp.upper_bytes,
-                 mp.nregs, mp.use_tma);
+                 mp.nregs, mp.use_tma, m_static_geometry(mp) ? "compile-time" : "run-time");
         return RECNEXT_OK;
     }
     WPlan wp;

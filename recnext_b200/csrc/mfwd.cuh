@@ -220,7 +220,7 @@ __device__ __forceinline__ void m_build_frags(const MPlan& pl, const MPlan& rt, 
         const long ch = (long)cg * pl.G + p;
         float v[2] = {0.f, 0.f};
         if (reg < 20) {
-            if (pl.L > 0 && (reg & 3) != 3) {
+            if (pl.L > 0 && a.w[0] != nullptr && (reg & 3) != 3) {
                 const int r = reg >> 2, kbase = 2 * t4 + 8 * (reg & 3);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -233,7 +233,7 @@ __device__ __forceinline__ void m_build_frags(const MPlan& pl, const MPlan& rt, 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int s = kbase + e - gq;
-                if (s >= 0 && s <= 4) v[e] = rc_load_param(a.w[1 + j], rt.wdtype, ch * 25 + r * 5 + s);
+                if (s >= 0 && s <= 4 && a.w[1 + j] != nullptr) v[e] = rc_load_param(a.w[1 + j], rt.wdtype, ch * 25 + r * 5 + s);
             }
         }
         tab[idx] = MmaT<T>::pack(v[0], v[1]);
@@ -284,6 +284,30 @@ __device__ __forceinline__ void m_repack(const MTeam<T>& tm, const T* __restrict
                 const uint32_t drow = b.row(i + 2) + 4u;
                 const unsigned short* srow = s16 + (g * H + i) * W;
                 for (int jj = j; jj < W; jj += LW) m_sts16(drow + 2u * jj, srow[jj]);
+            }
+        }
+    }
+}
+
+// variant 2: the external low-resolution operand z (dense planes in global memory) -> T of level 1, with the
+// replicate border columns the interpolation stages expect
+template <typename T>
+__device__ __forceinline__ void m_load_z(const MTeam<T>& tm, const T* __restrict__ z) {
+    const MPlan& pl = tm.pl;
+    const MLevel& lz = pl.lv[1];
+    const int LW = 1 << tm.rt.z_shift, RG = pl.team_lanes >> tm.rt.z_shift;
+    const int j = tm.tl & (LW - 1), rg = tm.tl >> tm.rt.z_shift;
+    const unsigned short* z16 = reinterpret_cast<const unsigned short*>(z);
+    for (int g = 0; g < pl.G; ++g) {
+        const uint32_t Tb = tm.tbuf(g);
+        for (int i = rg; i < lz.H; i += RG) {
+            const uint32_t trow = Tb + (uint32_t)(i * lz.tpB) + 4u;
+            const unsigned short* srow = z16 + ((long)g * lz.H + i) * lz.W;
+            for (int c = j; c < lz.W; c += LW) {
+                const uint32_t v = srow[c];
+                m_sts16(trow + 2u * c, v);
+                if (c == 0) m_sts16(trow - 2u, v);
+                if (c == lz.W - 1) m_sts16(trow + 2u * c + 2u, v);
             }
         }
     }
@@ -394,6 +418,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
     const uint32_t smem32 = rc_smem_u32(smem);
     MTeam<T> tm{pl, rt, smem32, smem32 + (uint32_t)(pl.smTeams + team * pl.team_bytes), team, wt, lane, wt * 32 + lane};
     const int L = LS >= 0 ? LS : pl.L, G = pl.G;
+    const int variant = LS >= 0 ? 0 : rt.variant;   // the specialised kernels serve RecConv2d only
     const int lg = lane >> 2, lt = lane & 3;
 
     // ---- CTA init: zero the team slices (the borders of the padded buffers stay zero), interpolation tables, mbarriers
@@ -438,6 +463,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
         const long cg_end = ((long)(cg + 1) * rt.B) < end ? ((long)(cg + 1) * rt.B) : end;
         for (; my < cg_end; my += pl.NTEAM) {
             const long p0 = plane0_of(my);
+            const long pidx = p0 / plane_elems;     // index of the batch's first (n, c) plane
             const long nxt = my + pl.NTEAM;
             // ---- x -> padded level 0
             if (rt.use_tma) {
@@ -445,9 +471,11 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                 phase ^= 1u;
                 m_repack<T>(tm, reinterpret_cast<const T*>(raw));
                 tm.sync();
-                if (L == 0) {
+                if (L == 0 || variant == 1) {
                     rc_fence_proxy_async();  // generic reads of `raw` before the next bulk copy's writes
                     if (nxt < end) issue_load(nxt);
+                } else if (variant == 2) {
+                    // level 1 is not materialised; T is filled below
                 } else {
                     // the raw batch landed on top of levels >= 1: restore their zero borders
                     const uint4 zero = {0u, 0u, 0u, 0u};
@@ -462,8 +490,48 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                 tm.sync();
             }
             // ---- down chain: x_l = down(x_{l-1})   (model/recnext.py:27-29)
+            if (variant == 1) {  // RecAttn2d.down[0] (model/recattn.py:60): x_1 = down(x) straight to global memory
+                const MLevel& lo = pl.lv[1];
+                for (int g = 0, mt = wt; g < G; mt += pl.TW) {
+                    if (mt >= lo.MT) { mt -= lo.MT + pl.TW; ++g; continue; }
+                    const MBuf in = tm.buf(g, 0);
+                    const int i0 = mt * 16, Ho = lo.H, Wo = lo.W;
+                    const int ia = i0 + lg, ib = ia + 8;
+                    T* dst = gy + (pidx + g) * (long)(Ho * Wo) + 2 * lt;
+                    const bool even = (Wo & 1) == 0;
+                    m_conv_rows<T, true>(in, lo.ntc, i0, lo.NT, tm.frag(g, 0), tm.bias(g, 0), lane, [&](int q, const float (&acc)[4]) {
+                        const int c = 8 * q + 2 * lt;
+                        if (c < Wo) {
 #pragma unroll
-            for (int l = 1; l <= L; ++l) {
+                            for (int h = 0; h < 2; ++h) {
+                                const int i = h ? ib : ia;
+                                if (i < Ho) {
+                                    const uint32_t w = MmaT<T>::pack(acc[2 * h], acc[2 * h + 1]);
+                                    T* d = dst + i * Wo + 8 * q;
+                                    if (even) *reinterpret_cast<uint32_t*>(d) = w;
+                                    else {
+                                        *reinterpret_cast<unsigned short*>(d) = (unsigned short)(w & 0xffffu);
+                                        if (c + 1 < Wo) *reinterpret_cast<unsigned short*>(d + 1) = (unsigned short)(w >> 16);
+                                    }
+                                }
+                            }
+                        }
+                    });
+                }
+                tm.sync();  // level 0 is rewritten by the next batch's repack
+                continue;
+            }
+            if (variant == 2) {  // RecAttn2d tail (model/recattn.py:67): s_0 = x + interpolate(z); y = conv(s_0)
+                m_load_z<T>(tm, reinterpret_cast<const T*>(a.gy) + pidx * (long)(pl.lv[1].H * pl.lv[1].W));
+                tm.sync();
+                const MLevel& lv = pl.lv[1];
+                if (lv.exact2x && pl.mode == 0 && !(rt.dbg & 1)) m_up2x_add<T>(tm, 1);
+                else m_up_add<T>(tm, smem, 1);
+                tm.sync();
+            }
+            const int Lp = variant == 2 ? 0 : L;  // levels of the pyramid proper
+#pragma unroll
+            for (int l = 1; l <= Lp; ++l) {
                 const MLevel& lo = pl.lv[l];
                 for (int g = 0, mt = wt; g < G; mt += pl.TW) {
                     if (mt >= lo.MT) { mt -= lo.MT + pl.TW; ++g; continue; }
@@ -486,7 +554,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
             }
             // ---- up pass: t_l = convs[L-l](s_l); s_{l-1} = x_{l-1} + interpolate(t_l)   (model/recnext.py:31-33)
 #pragma unroll
-            for (int l = L; l >= 1; --l) {
+            for (int l = Lp; l >= 1; --l) {
                 const MLevel& lv = pl.lv[l];
                 for (int g = 0, mt = wt; g < G; mt += pl.TW) {
                     if (mt >= lv.MT) { mt -= lv.MT + pl.TW; ++g; continue; }
@@ -575,7 +643,7 @@ __global__ void __launch_bounds__(512, 1) recconv_mfwd_static_kernel(const __gri
 template <typename T, int H0, int W0, int L0, int G0>
 inline bool m_try_static(const MPlan& pl, const KernelArgs& a, cudaStream_t stream, cudaError_t& err) {
     constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1);
-    if (pl.H != H0 || pl.W != W0 || pl.L != L0 || pl.G != G0) return false;
+    if (pl.variant != 0 || pl.H != H0 || pl.W != W0 || pl.L != L0 || pl.G != G0) return false;
     const MPlan st = m_static_patched(sp, pl);
     if (memcmp(&st, &pl, sizeof(MPlan)) != 0) return false;
     static int configured = 0;  // benign race: idempotent
@@ -587,6 +655,19 @@ inline bool m_try_static(const MPlan& pl, const KernelArgs& a, cudaStream_t stre
     recconv_mfwd_static_kernel<T, H0, W0, L0, G0><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
     err = cudaGetLastError();
     return true;
+}
+
+// true if the run-time plan is one of the compile-time geometries (introspection: recconv_plan_describe)
+template <int H0, int W0, int L0, int G0>
+inline bool m_matches_static(const MPlan& pl) {
+    constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, 1);
+    if (pl.variant != 0 || pl.dtype != 1 || pl.H != H0 || pl.W != W0 || pl.L != L0 || pl.G != G0) return false;
+    const MPlan st = m_static_patched(sp, pl);
+    return memcmp(&st, &pl, sizeof(MPlan)) == 0;
+}
+inline bool m_is_static(const MPlan& pl) {
+    return !(pl.dbg & 2) && (m_matches_static<56, 56, 4, 1>(pl) || m_matches_static<28, 28, 3, 1>(pl) || m_matches_static<14, 14, 2, 4>(pl) ||
+                             m_matches_static<7, 7, 1, 8>(pl));
 }
 
 template <typename T>

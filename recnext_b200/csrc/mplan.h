@@ -39,6 +39,9 @@ struct MLevel {
 
 struct MPlan {
     int B, C, H, W, L, mode, dtype, wdtype, has_bias;
+    int variant;         // 0: RecConv2d forward; 1: `down` only (x -> x_1 in global memory: RecAttn2d.down[0]);
+                         // 2: y = conv(x + interpolate(z)) with an external low-resolution operand z (RecAttn2d tail)
+    int z_shift;         // variant 2: lane mapping of the z -> T copy (lanes per row group = 1 << z_shift)
     int G, TW, NTEAM, threads, team_lanes;
     int n_cg;
     int use_tma;
@@ -61,6 +64,7 @@ struct MPlan {
 
 struct MPlanOptions {
     int force_G = 0, force_TW = 0, force_NT = 0, force_no_tma = 0, max_warps = 16, dbg = 0;
+    int variant = 0, zH = 0, zW = 0;   // variant 2: size of the external operand z (becomes level 1)
     int num_sms = 148;
     int smem_limit = 227 * 1024;
 };
@@ -83,8 +87,14 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
     pl = MPlan{};
     pl.B = B; pl.C = C; pl.H = H; pl.W = W; pl.L = L; pl.mode = mode; pl.dtype = dtype; pl.wdtype = wdtype; pl.has_bias = has_bias;
     pl.dbg = opt.dbg;
+    pl.variant = opt.variant;
+    if (opt.variant != 0 && L != 1) return 2;
     pl.lv[0].H = H; pl.lv[0].W = W;
     for (int l = 1; l <= L; ++l) { pl.lv[l].H = rc_down_size(pl.lv[l - 1].H, 5); pl.lv[l].W = rc_down_size(pl.lv[l - 1].W, 5); }
+    if (opt.variant == 2) {
+        if (opt.zH < 1 || opt.zW < 1 || opt.zH > 1023 || opt.zW > 1023) return 2;
+        pl.lv[1].H = opt.zH; pl.lv[1].W = opt.zW;
+    }
     for (int l = 0; l <= L; ++l) {
         MLevel& g = pl.lv[l];
         g.NT = rc_div_up(g.W, 8); g.MT = rc_div_up(g.H, 16);
@@ -170,6 +180,7 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
 
     // lane mappings of the element-wise stages: (row group, column pair)
     pl.rp_shift = m_lane_shift((W & 1) ? W : W / 2, pl.team_lanes);
+    pl.z_shift = opt.variant == 2 ? m_lane_shift(pl.lv[1].W, pl.team_lanes) : 0;
     for (int l = 1; l <= L; ++l) {
         pl.lv[l].up_shift = m_lane_shift((pl.lv[l - 1].W + 1) / 2, pl.team_lanes);
         pl.lv[l].up_rpg = rc_div_up(pl.lv[l].H, pl.team_lanes >> pl.lv[l].up_shift);

@@ -1,0 +1,188 @@
+"""RecAttn2d — drop-in for the reference A-series token mixer (reference model/recattn.py:54-67).
+
+    forward(x) = conv(x + interpolate(LinearAttention(down_conv(x)), size=x.shape[2:], mode))
+
+Same constructor, sub-module names and ``state_dict`` layout as the reference (``down.0`` ConvNorm k x k stride 2,
+``down.1`` LinearAttention1/2 with ``qk`` / ``pe`` ConvNorms, ``conv`` ConvNorm), including ``ConvNorm.fuse()``
+(model/recattn.py:87-111) so fused-BN eval checkpoints load unchanged.
+
+What runs where:
+  * the two plane-independent, memory-bound pieces — the stride-2 depthwise conv and the fused
+    ``conv(x + interpolate(z))`` tail — run in the hand-written sm_100a tensor-core kernels behind
+    ``recattn_down_forward`` / ``recattn_up_forward`` (include/recnext_b200.h), BatchNorm folded into (w, b);
+  * the linear attention in between mixes channels (1x1 grouped conv, d x d contractions): plain batched GEMMs,
+    left to the library (torch.matmul / cuBLAS) exactly as the reference writes them (model/recattn.py:16-51).
+Inference only for now (16-bit CUDA activations, eval mode): training through the custom kernels needs their
+backward, which is not built yet, so ``forward`` raises in training mode instead of silently falling back.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native as N
+from .recconv import _DTYPES, _MODES, _stream
+
+
+def _call_desc(x: torch.Tensor, mode: str, wdtype: torch.dtype, has_bias: bool) -> N.RecConvDesc:
+    if x.dim() != 4:
+        raise ValueError(f"RecAttn2d expects [B,C,H,W], got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("recnext_b200.RecAttn2d runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if x.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError(f"RecAttn2d kernels are built for 16-bit activations (bfloat16 / float16), got {x.dtype}")
+    B, C, H, W = x.shape
+    return N.RecConvDesc(B, C, H, W, 5, 1, _MODES[mode], _DTYPES[x.dtype], _DTYPES[wdtype], int(has_bias))
+
+
+def _prep(x, w, b):
+    if w.dtype != torch.float32 and w.dtype != x.dtype:
+        raise TypeError(f"RecAttn2d: parameters must be float32 or match the input dtype ({w.dtype} vs {x.dtype})")
+    w = w.detach().contiguous()
+    b = None if b is None else b.detach().to(w.dtype).contiguous()
+    if tuple(w.shape) != (x.shape[1], 1, 5, 5):
+        raise ValueError(f"RecAttn2d: depthwise 5x5 filter expected, got {tuple(w.shape)}")
+    return w, b
+
+
+def recattn_down_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """depthwise 5x5 stride-2 conv (+ bias) — RecAttn2d.down[0] with its BatchNorm folded (model/recattn.py:60)."""
+    x = x.contiguous()
+    d = _call_desc(x, "nearest", w.dtype, b is not None)
+    w, b = _prep(x, w, b)
+    B, C, H, W = x.shape
+    out = torch.empty(B, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().recattn_down_forward(ctypes.byref(d), w.data_ptr(), None if b is None else b.data_ptr(), x.data_ptr(),
+                                             out.data_ptr(), _stream(x)), "recattn_down_forward")
+    return out
+
+
+def recattn_up_forward(x: torch.Tensor, z: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: str = "nearest") -> torch.Tensor:
+    """conv(x + interpolate(z, size=x.shape[2:], mode)) — the tail of RecAttn2d.forward (model/recattn.py:67)."""
+    x = x.contiguous()
+    z = z.to(x.dtype).contiguous()
+    if z.dim() != 4 or z.shape[:2] != x.shape[:2]:
+        raise ValueError(f"RecAttn2d: z {tuple(z.shape)} does not match x {tuple(x.shape)}")
+    d = _call_desc(x, mode, w.dtype, b is not None)
+    w, b = _prep(x, w, b)
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().recattn_up_forward(ctypes.byref(d), w.data_ptr(), None if b is None else b.data_ptr(), x.data_ptr(), z.data_ptr(),
+                                           int(z.shape[2]), int(z.shape[3]), y.data_ptr(), _stream(x)), "recattn_up_forward")
+    return y
+
+
+class ConvNorm(nn.Sequential):
+    """Conv2d + BatchNorm2d with the reference's fuse() (model/recattn.py:70-111)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=0, dilation=1, groups=1, bias=False, bn_weight_init=1):
+        super().__init__()
+        self.add_module("conv", nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias=bias))
+        self.add_module("norm", nn.BatchNorm2d(out_channels))
+        nn.init.constant_(self.norm.weight, bn_weight_init)
+        nn.init.constant_(self.norm.bias, 0)
+
+    @torch.no_grad()
+    def folded(self):
+        """(w, b) of the equivalent biased conv (eval-mode BatchNorm folded), fp32"""
+        s = self.norm.weight / (self.norm.running_var + self.norm.eps) ** 0.5
+        b = self.norm.bias - s * self.norm.running_mean
+        if self.conv.bias is not None:
+            b = b + s * self.conv.bias
+        return (s[:, None, None, None] * self.conv.weight).float(), b.float()
+
+    @torch.no_grad()
+    def fuse(self):
+        w, b = self.folded()
+        c = self.conv
+        m = nn.Conv2d(w.size(1) * c.groups, w.size(0), w.shape[2:], stride=c.stride, padding=c.padding, dilation=c.dilation,
+                      groups=c.groups, device=c.weight.device)
+        m.weight.data.copy_(w)
+        m.bias.data.copy_(b)
+        return m
+
+
+def _wb(m):
+    """(w, b) of a ConvNorm (BatchNorm folded on the fly) or of the nn.Conv2d that fuse() left in its place"""
+    if isinstance(m, ConvNorm):
+        return m.folded()
+    return m.weight, m.bias
+
+
+class LinearAttention1(nn.Module):
+    """model/recattn.py:8-28 — kv formulation, O(n d^2)"""
+
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.qk = ConvNorm(dim, dim * 2, kernel_size=1, groups=2)
+        self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim)
+
+    def forward(self, x):
+        b, c, h, w = x.shape
+        n = h * w
+        s = n ** -0.5
+        qk = F.elu(self.qk(x)) + 1.0
+        (q, k), v = qk.view(b, 2, self.num_heads, self.head_dim, n).unbind(dim=1), x
+        q_t = q.transpose(-1, -2)
+        kv = (k * s) @ (v.view(b, self.num_heads, self.head_dim, n).transpose(-1, -2) * s)
+        x = q_t @ kv / (q_t @ k.mean(dim=-1, keepdim=True) + 1e-6)
+        return x.transpose(-1, -2).reshape(b, c, h, w) + self.pe(v)
+
+
+class LinearAttention2(nn.Module):
+    """model/recattn.py:31-51 — quadratic formulation, used where n is tiny (stage 3)"""
+
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.qk = ConvNorm(dim, dim * 2, kernel_size=1, groups=2)
+        self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim)
+
+    def forward(self, x):
+        b, c, h, w = x.shape
+        n = h * w
+        s = n ** -0.5
+        qk = F.elu(self.qk(x)) + 1.0
+        (q, k), v = qk.view(b, 2, self.num_heads, self.head_dim, n).unbind(dim=1), x
+        qk = q.transpose(-1, -2) @ k
+        qk = qk / (qk.mean(dim=-1, keepdim=True) + 1e-6)
+        x = (qk * s) @ (v.view(b, self.num_heads, self.head_dim, n).transpose(-1, -2) * s)
+        return x.transpose(-1, -2).reshape(b, c, h, w) + self.pe(v)
+
+
+class RecAttn2d(nn.Module):
+    """``RecAttn2d(dim, num_heads, kernel_size=5, stage=1, mode='nearest')`` — reference model/recattn.py:54-67."""
+
+    def __init__(self, dim, num_heads, kernel_size=5, stage=1, mode="nearest"):
+        super().__init__()
+        if kernel_size != 5:
+            raise ValueError("RecAttn2d: the CUDA kernels are built for kernel_size 5 (the reference's value)")
+        if mode not in _MODES:
+            raise ValueError(f"RecAttn2d: mode {mode!r} not supported (bilinear, nearest)")
+        self.mode = mode
+        LinearAttention = LinearAttention2 if stage >= 3 else LinearAttention1
+        self.down = nn.Sequential(
+            ConvNorm(dim, dim, kernel_size=kernel_size, padding=kernel_size // 2, stride=2, groups=dim),
+            LinearAttention(dim=dim, num_heads=num_heads),
+        )
+        self.conv = ConvNorm(dim, dim, kernel_size=kernel_size, padding=kernel_size // 2, groups=dim)
+
+    def forward(self, x):
+        if self.training:
+            raise RuntimeError("recnext_b200.RecAttn2d: the sm_100a kernels have no backward yet — call .eval() "
+                               "(inference with BatchNorm folded); there is deliberately no PyTorch fallback")
+        if torch.is_autocast_enabled() and x.is_cuda:
+            x = x.to(torch.get_autocast_dtype("cuda"))
+        wd, bd = _wb(self.down[0])
+        wc, bc = _wb(self.conv)
+        low = recattn_down_forward(x, wd, bd)                 # model/recattn.py:60
+        z = self.down[1](low)                                 # linear attention: library GEMMs, as the reference writes it
+        return recattn_up_forward(x, z, wc, bc, self.mode)    # model/recattn.py:67

@@ -223,3 +223,28 @@ def test_team_plan_covers_every_plane_exactly_once():
         x = rng.standard_normal((B, C, H, W), dtype=np.float32)
         y, plan = emu.run(x, p, "bilinear", opts=opts, team=True)
         assert rel_err(y, O.forward(x, p, "bilinear")) < TOL_FP32, plan  # a skipped plane would stay zero
+
+
+def test_tensor_core_plan_selection(native):
+    """16-bit activations with k = 5 take the tensor-core forward (compile-time geometry for the RecNeXt stage shapes);
+    fp32, k != 5, tiny planes and the backward stay on the FMA kernels."""
+    import torch
+
+    from recnext_b200 import recconv
+
+    d = lambda shape, L, dt, k=5, bwd=False: recconv.plan_describe(shape, k, L, "bilinear", dt, False, bwd)  # noqa: E731
+    for shape, L in [((256, 64, 56, 56), 4), ((256, 128, 28, 28), 3), ((256, 256, 14, 14), 2), ((128, 80, 56, 56), 4)]:
+        s = d(shape, L, torch.bfloat16)
+        assert "tensor-core" in s and "geometry=compile-time" in s, s
+    assert "geometry=run-time" in d((2, 128, 100, 168), 3, torch.bfloat16)
+    assert "geometry=run-time" in d((4, 64, 56, 56), 4, torch.float16)
+    assert "tensor-core" not in d((256, 512, 7, 7), 1, torch.bfloat16)      # smaller than one MMA tile
+    assert "tensor-core" not in d((256, 64, 56, 56), 4, torch.float32)
+    assert "tensor-core" not in d((4, 64, 56, 56), 4, torch.bfloat16, k=7)
+    assert "tensor-core" not in d((4, 64, 56, 56), 4, torch.bfloat16, bwd=True)
+    # teams fill the SM: at least 8 warps for every stage shape
+    import re
+    for shape, L in [((256, 64, 56, 56), 4), ((256, 128, 28, 28), 3), ((256, 256, 14, 14), 2), ((2, 128, 100, 168), 3)]:
+        s = d(shape, L, torch.bfloat16)
+        assert int(re.search(r"threads=(\d+)", s).group(1)) >= 256, s
+        assert int(re.search(r"smem=(\d+)", s).group(1)) <= 227 * 1024, s

@@ -1,0 +1,127 @@
+"""RecAttn2d (A-series token mixer, reference model/recattn.py:54-67): state_dict layout and host logic on CPU, parity of
+the two CUDA pieces and of the whole module against fixtures generated from the UNMODIFIED reference
+(oracle/gen_golden_recattn.py) on the GPU."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import GOLDEN, TOL_BF16, rel_err
+
+FIX = sorted(glob.glob(os.path.join(GOLDEN, "recattn_*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    B, dim, heads, H, W, stage, mode = (int(v) for v in z["meta"])
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd:")}
+    return z, dict(B=B, dim=dim, heads=heads, H=H, W=W, stage=stage, mode=["bilinear", "nearest"][mode]), sd
+
+
+def _module(meta, sd):
+    from recnext_b200.recattn import RecAttn2d
+
+    m = RecAttn2d(meta["dim"], meta["heads"], stage=meta["stage"], mode=meta["mode"])
+    m.load_state_dict(sd, strict=True)  # same keys and shapes as the reference module
+    return m.eval()
+
+
+def test_fixtures_exist():
+    assert len(FIX) >= 5
+
+
+@pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
+def test_state_dict_layout_matches_reference(path):
+    _, meta, sd = _load(path)
+    m = _module(meta, sd)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    # LinearAttention2 where the reference uses it (stage >= 3, model/recattn.py:58)
+    assert type(m.down[1]).__name__ == ("LinearAttention2" if meta["stage"] >= 3 else "LinearAttention1")
+
+
+@pytest.mark.parametrize("path", FIX[:2], ids=lambda p: os.path.basename(p)[8:-4])
+def test_convnorm_fold_and_fuse_match_reference_pieces(path):
+    """host logic on CPU: folding BatchNorm (model/recattn.py:87-111) reproduces the reference's ConvNorm output"""
+    z, meta, sd = _load(path)
+    m = _module(meta, sd)
+    w, b = m.down[0].folded()
+    x = torch.from_numpy(z["x"])
+    low = F.conv2d(x, w, b, stride=2, padding=2, groups=meta["dim"])
+    assert rel_err(low.numpy(), z["low"]) < 1e-5
+    fused = m.down[0].fuse()
+    assert rel_err(fused(x).detach().numpy(), z["low"]) < 1e-5
+    # the linear attention mirror (library ops) against the reference's z, on CPU fp32
+    with torch.no_grad():
+        zz = m.down[1](torch.from_numpy(z["low"]))
+    assert rel_err(zz.numpy(), z["z"]) < 1e-5
+
+
+def test_no_fallbacks():
+    from recnext_b200.recattn import RecAttn2d
+
+    m = RecAttn2d(8, 2)
+    with pytest.raises(RuntimeError, match="no backward"):
+        m(torch.randn(1, 8, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(torch.randn(1, 8, 8, 8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_cuda_pieces_against_reference(path, dtype):
+    from recnext_b200.recattn import recattn_down_forward, recattn_up_forward
+
+    z, meta, sd = _load(path)
+    m = _module(meta, sd).cuda()
+    tol = TOL_BF16 if dtype == torch.bfloat16 else 4e-3
+    x = torch.from_numpy(z["x"]).cuda().to(dtype)
+    wd, bd = m.down[0].folded()
+    low = recattn_down_forward(x, wd, bd)
+    assert low.shape == tuple(z["low"].shape) or tuple(low.shape) == tuple(z["low"].shape)
+    assert rel_err(low.float().cpu().numpy(), z["low"]) < tol
+    wc, bc = m.conv.folded()
+    y = recattn_up_forward(x, torch.from_numpy(z["z"]).cuda(), wc, bc, meta["mode"])
+    assert rel_err(y.float().cpu().numpy(), z["y"]) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
+def test_cuda_module_against_reference(path):
+    z, meta, sd = _load(path)
+    m = _module(meta, sd).cuda()
+    x = torch.from_numpy(z["x"]).cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x)
+    assert y.dtype == torch.bfloat16
+    assert rel_err(y.float().cpu().numpy(), z["y"]) < TOL_BF16
+    # fused-BN form (ConvNorm -> Conv2d with bias, what replace_batchnorm leaves): same result
+    m.down[0] = m.down[0].fuse()
+    m.conv = m.conv.fuse()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = m(x)
+    assert rel_err(y2.float().cpu().numpy(), y.float().cpu().numpy()) < 1e-2
+
+
+@pytest.mark.gpu
+def test_cuda_full_size_a3_stage_shapes():
+    """BASELINE config 4 (A3, batch 256 at 224^2) stage shapes: both pieces against PyTorch bf16 on the same inputs"""
+    from recnext_b200.recattn import recattn_down_forward, recattn_up_forward
+
+    for (B, C, H) in [(256, 64, 56), (256, 128, 28), (256, 256, 14), (256, 512, 7)]:
+        torch.manual_seed(C)
+        x = torch.randn(B, C, H, H, device="cuda").bfloat16()
+        w = torch.empty(C, 1, 5, 5, device="cuda").uniform_(-0.2, 0.2)
+        b = torch.empty(C, device="cuda").uniform_(-0.2, 0.2)
+        low = recattn_down_forward(x, w, b)
+        ref = F.conv2d(x.float(), w, b, stride=2, padding=2, groups=C)
+        assert rel_err(low.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
+        zz = torch.randn(B, C, (H + 1) // 2, (H + 1) // 2, device="cuda").bfloat16()
+        y = recattn_up_forward(x, zz, w, b, "nearest")
+        ref = F.conv2d(x.float() + F.interpolate(zz.float(), size=(H, H), mode="nearest"), w, b, padding=2, groups=C)
+        assert rel_err(y.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16

@@ -1,0 +1,167 @@
+"""GPU parity tests of the TENSOR-CORE forward (16-bit activations, k = 5; recnext_b200/csrc/mfwd.cuh).
+
+The path rounds every intermediate where the reference's autocast graph rounds it (conv outputs, `f + x`,
+interpolate; reference model/recnext.py:24-34), so besides the 2e-2 bar against the fp32 oracle it must agree with
+PyTorch's own bf16 result almost element for element.  The FMA kernels stay reachable with RECNEXT_PATH=fma and are
+exercised in a subprocess (the choice is read once per process).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import recconv_oracle as O
+from tests.helpers import TOL_BF16, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torch_lowp(x, ws, bs, L, mode):
+    """the reference forward (model/recnext.py:24-34) on PyTorch CUDA in x.dtype: every op rounds to x.dtype"""
+    C, dt = x.shape[1], x.dtype
+    c = lambda t: None if t is None else t.to(dt)  # noqa: E731
+    b = (lambda j: c(bs[j])) if bs is not None else (lambda j: None)
+    feats, cur = [], x
+    for _ in range(L):
+        size = cur.shape[2:]
+        cur = F.conv2d(cur, c(ws[0]), b(0), stride=2, padding=2, groups=C)
+        feats.append((cur, size))
+    up = 0
+    for j, (f, size) in enumerate(reversed(feats)):
+        up = F.interpolate(F.conv2d(f + up, c(ws[1 + j]), b(1 + j), padding=2, groups=C), size=size, mode=mode)
+    return F.conv2d(x + up, c(ws[1 + L]), b(1 + L), padding=2, groups=C)
+
+
+def _params(C, L, bias, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    ws = [torch.empty(C, 1, 5, 5, device=DEV).uniform_(-0.2, 0.2, generator=g) for _ in range(L + 2)]
+    bs = [torch.empty(C, device=DEV).uniform_(-0.2, 0.2, generator=g) for _ in range(L + 2)] if bias else None
+    return ws, bs
+
+
+def test_mma_path_is_selected():
+    import recnext_b200 as R
+    from recnext_b200 import recconv
+
+    d = recconv.plan_describe((256, 64, 56, 56), 5, 4, "bilinear", torch.bfloat16, False, False)
+    assert "tensor-core" in d and "geometry=compile-time" in d, d
+    d = recconv.plan_describe((2, 128, 100, 168), 5, 3, "bilinear", torch.bfloat16, False, False)
+    assert "tensor-core" in d and "geometry=run-time" in d, d
+    assert "tensor-core" not in recconv.plan_describe((256, 64, 56, 56), 5, 4, "bilinear", torch.float32, False, False)
+    assert R is not None
+
+
+# B, C, H, W, L, mode, bias — stage shapes (compile-time geometry), detection shapes, ragged / odd / tiny (run-time)
+_CASES = [
+    (32, 64, 56, 56, 4, "bilinear", False), (32, 128, 28, 28, 3, "bilinear", True), (32, 256, 14, 14, 2, "bilinear", False),
+    (3, 64, 56, 56, 4, "nearest", True), (2, 80, 56, 56, 4, "bilinear", False), (2, 128, 100, 168, 3, "bilinear", False),
+    (2, 128, 100, 167, 3, "bilinear", True), (2, 256, 50, 84, 2, "bilinear", False), (2, 512, 25, 42, 1, "bilinear", True),
+    (1, 7, 25, 21, 3, "bilinear", True), (1, 16, 96, 96, 4, "bilinear", False), (3, 6, 12, 10, 0, "bilinear", True),
+    (2, 4, 33, 65, 5, "nearest", False), (1, 2, 10, 300, 2, "bilinear", False),
+]
+
+
+@pytest.mark.parametrize("case", _CASES, ids=lambda c: "x".join(str(v) for v in c))
+def test_mma_forward_vs_torch_bf16_and_fp32(case):
+    import recnext_b200 as R
+
+    B, C, H, W, L, mode, bias = case
+    torch.manual_seed(B * 131 + C + H)
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    ws, bs = _params(C, L, bias, 7)
+    y = R.recconv_forward(x, ws, bs, 5, L, mode)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y32 = _torch_lowp(x.float(), ws, bs, L, mode)
+        ylo = _torch_lowp(x, ws, bs, L, mode)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert rel_err(y.float().cpu().numpy(), y32.cpu().numpy()) < TOL_BF16        # the north_star bar
+    assert rel_err(y.float().cpu().numpy(), ylo.float().cpu().numpy()) < TOL_BF16
+    # same rounding points as the reference graph: (nearly) every element is bit-identical to PyTorch's bf16 result.
+    # (With a bias PyTorch's cuDNN route adds it in a second bf16 op — a backend detail; we add it in fp32 before the
+    # single rounding, which is the closer of the two to the fp32 oracle — so the bit-level check is for bias=False.)
+    if not bias:
+        assert float((y == ylo).float().mean()) > 0.99
+
+
+def test_mma_forward_vs_c_oracle_bf16():
+    """against the C oracle (fp64 tap sums) on bf16-representable inputs and parameters"""
+    import recnext_b200 as R
+
+    rng = np.random.default_rng(11)
+    B, C, H, W, L = 2, 16, 28, 28, 3
+    p = O.RecConvParams.random(C, 5, L, True, rng)
+    r16 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).bfloat16().float().numpy()  # noqa: E731
+    p = O.RecConvParams(down_w=r16(p.down_w), convs_w=[r16(w) for w in p.convs_w], down_b=r16(p.down_b), convs_b=[r16(b) for b in p.convs_b])
+    x = r16(rng.standard_normal((B, C, H, W), dtype=np.float32))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    ws = [t(p.down_w)] + [t(w) for w in p.convs_w]
+    bs = [t(p.down_b)] + [t(b) for b in p.convs_b]
+    y = R.recconv_forward(t(x).bfloat16(), ws, bs, 5, L, "bilinear")
+    assert rel_err(y.float().cpu().numpy(), O.forward(x, p, "bilinear")) < TOL_BF16
+
+
+def test_mma_forward_fp16():
+    import recnext_b200 as R
+
+    torch.manual_seed(5)
+    x = (0.5 * torch.randn(4, 32, 56, 56, device=DEV)).half()
+    ws, bs = _params(32, 4, True, 3)
+    y = R.recconv_forward(x, ws, bs, 5, 4, "bilinear")
+    y32 = _torch_lowp(x.float(), ws, bs, 4, "bilinear")
+    assert rel_err(y.float().cpu().numpy(), y32.cpu().numpy()) < 4e-3
+
+
+def test_mma_batch_slices_and_determinism_full_size():
+    """BASELINE config-2 stage-0 size: images are independent, results are reproducible bit for bit"""
+    import recnext_b200 as R
+
+    torch.manual_seed(9)
+    x = torch.randn(256, 64, 56, 56, device=DEV).bfloat16()
+    ws, _ = _params(64, 4, False, 1)
+    y = R.recconv_forward(x, ws, None, 5, 4, "bilinear")
+    assert torch.equal(y, R.recconv_forward(x, ws, None, 5, 4, "bilinear"))
+    sl = slice(97, 131)
+    assert torch.equal(y[sl], R.recconv_forward(x[sl].contiguous(), ws, None, 5, 4, "bilinear"))
+    # unaligned input pointer (no TMA bulk copies): same bits
+    buf = torch.empty(x.numel() + 2, device=DEV, dtype=torch.bfloat16)
+    xu = buf[2:].view_as(x)
+    xu.copy_(x)
+    assert xu.data_ptr() % 16 != 0
+    assert torch.equal(y[:8], R.recconv_forward(xu[:8], ws, None, 5, 4, "bilinear"))
+
+
+def test_fma_path_still_serves_16bit_activations():
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "import recnext_b200 as R\n"
+        "from recnext_b200 import recconv\n"
+        "assert 'tensor-core' not in recconv.plan_describe((4, 64, 56, 56), 5, 4, 'bilinear', torch.bfloat16, False, False)\n"
+        "torch.manual_seed(0)\n"
+        "x = torch.randn(4, 64, 56, 56, device='cuda').bfloat16()\n"
+        "ws = [torch.empty(64, 1, 5, 5, device='cuda').uniform_(-0.2, 0.2) for _ in range(6)]\n"
+        "y = R.recconv_forward(x, ws, None, 5, 4, 'bilinear')\n"
+        "torch.save(y.cpu(), sys.argv[1]); torch.save([x.cpu()] + [w.cpu() for w in ws], sys.argv[2])\n" % ROOT
+    )
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        fy, fi = os.path.join(td, "y.pt"), os.path.join(td, "in.pt")
+        env = dict(os.environ, RECNEXT_PATH="fma")
+        subprocess.run([sys.executable, "-c", code, fy, fi], check=True, env=env, timeout=300)
+        y_fma = torch.load(fy)
+        ins = torch.load(fi)
+    import recnext_b200 as R
+
+    x, ws = ins[0].to(DEV), [w.to(DEV) for w in ins[1:]]
+    y_mma = R.recconv_forward(x, ws, None, 5, 4, "bilinear")
+    # FMA path keeps fp32 intermediates, the tensor-core path rounds like the reference: both within the bar of each other
+    assert rel_err(y_mma.float().cpu().numpy(), y_fma.float().numpy()) < TOL_BF16
