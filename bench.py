@@ -30,6 +30,18 @@ METRIC, UNIT = "RecNeXt-M3 inference images/sec (batch 256/GPU, 224x224, bf16, f
 WORKLOAD = "RecNeXt-M3 inference, batch 256 at 224x224 bf16, fused-BN eval model (BASELINE.json configs[1])"
 
 
+def select_model(name: str):
+    """--model recnext_a3 measures BASELINE.json configs[3] (A-series) with the same contract; the default is configs[1]."""
+    global MODEL, METRIC, WORKLOAD
+    if name == MODEL:
+        return
+    MODEL = name
+    tag = name.split("_")[1].upper()
+    METRIC = f"RecNeXt-{tag} inference images/sec (batch 256/GPU, 224x224, bf16, fused-BN eval)"
+    cfg = "configs[3]" if tag.startswith("A") else "configs[1] shape, other width/depth"
+    WORKLOAD = f"RecNeXt-{tag} inference, batch 256 at 224x224 bf16, fused-BN eval model (BASELINE.json {cfg})"
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -84,11 +96,11 @@ def build_cpu_reference_model():
     BN folded) — what a user of the reference gets on the host."""
     import torch
 
-    from oracle.torch_ref import RefRecConv2d
+    from oracle.torch_ref import RefRecAttn2d, RefRecConv2d
     from recnext_b200.model import create_model, replace_batchnorm
 
     torch.manual_seed(0)
-    net = create_model(MODEL, token_mixer=RefRecConv2d).eval()
+    net = create_model(MODEL, token_mixer=RefRecAttn2d if "_a" in MODEL else RefRecConv2d).eval()
     replace_batchnorm(net)
     return net
 
@@ -165,9 +177,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--model", default=MODEL, help="recnext_m0..m5 / recnext_a0..a5 (default: the metric's recnext_m3)")
     ap.add_argument("--memory-format", default="contiguous", choices=["contiguous", "channels_last"],
                     help="memory format of the model around RecConv2d (the RecConv kernels always work on NCHW planes)")
     args = ap.parse_args()
+    select_model(args.model)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -256,9 +270,12 @@ def main():
         g["bytes"] += rec["bytes"]; g["ms"] += rec["ms"]; g["n"] += 1
     per_shape, dom = [], {"bytes": 0, "ms": 0.0, "n": 0}
     for shape, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
-        level = {56: 4, 28: 3, 14: 2, 7: 1}.get(shape[2], 0) if RES == 224 else None
-        desc = RC.plan_describe(shape, 5, level, "bilinear", torch.bfloat16, False, False) if level is not None else ""
-        kern = "recconv_mfwd_static_kernel" if "compile-time" in desc else ("recconv_mfwd_kernel" if "tensor-core" in desc else "recconv_wfwd_kernel")
+        if isinstance(shape[0], str):   # RecAttn2d pieces: ("down" | "up", B, C, H, W)
+            kern = "recconv_mfwd_kernel/" + shape[0]
+        else:
+            level = {56: 4, 28: 3, 14: 2, 7: 1}.get(shape[2], 0) if RES == 224 else None
+            desc = RC.plan_describe(shape, 5, level, "bilinear", torch.bfloat16, False, False) if level is not None else ""
+            kern = "recconv_mfwd_static_kernel" if "compile-time" in desc else ("recconv_mfwd_kernel" if "tensor-core" in desc else "recconv_wfwd_kernel")
         gbs = g["bytes"] / (g["ms"] * 1e-3) * 1e-9 if g["ms"] > 0 else 0.0
         per_shape.append({"shape": list(shape), "kernel": kern, "launches_per_step": g["n"] / max(args.steps, 1),
                           "avg_launch_ms": round(g["ms"] / g["n"], 5), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
@@ -277,7 +294,8 @@ def main():
         pass
     roofline = {
         "bound": "hbm",
-        "kernel": "recnext::recconv_mfwd_static_kernel<bf16> (tensor-core fused RecConv forward; its %d launches of the timed steps)" % dom["n"],
+        "kernel": "recnext::recconv_mfwd%s_kernel<bf16> (tensor-core fused %s forward; its %d launches of the timed steps)"
+                  % (("", "RecAttn2d down / up-add-conv", dom["n"]) if "_a" in MODEL else ("_static", "RecConv", dom["n"])),
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
         "peak_source": peak_src, "bytes_per_launch": dom["bytes"] / max(dom["n"], 1), "avg_launch_ms": dom["ms"] / max(dom["n"], 1),
         "share_of_step": round(dom["ms"] / ms_total, 4), "all_recconv_share_of_step": round(kern_all_ms / ms_total, 4),
@@ -305,7 +323,7 @@ def main():
         "gpu_launches": n_launch,
         "roofline": roofline,
     }
-    if not args.no_micro:
+    if not args.no_micro and "_a" not in MODEL:
         out["recconv_fwd_bwd"] = recconv_microbench(torch, R, peak)
     if not args.no_cpu_baseline:
         rate, ms, threads = cpu_reference_rate(steps=3, warmup=1, batch=16)

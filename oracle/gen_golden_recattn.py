@@ -52,5 +52,30 @@ def main():
         print(name, tuple(y.shape), float(y.abs().mean()))
 
 
+
+
+def model_logits_a():
+    """RecNeXt-A0 eval logits with the name-keyed deterministic weights of oracle/detinit.py (reference model/recattn.py)."""
+    sys.path.insert(0, ROOT)
+    from timm.models import create_model  # shim
+
+    from oracle.detinit import fill_state_dict_
+
+    d = {}
+    net = create_model("recnext_a0").eval()
+    fill_state_dict_(net, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        d["recnext_a0_224_logits"] = net(x).numpy()
+        d["recnext_a0_224_feat_mean"] = net.forward_features(x).mean((2, 3)).numpy()
+    d["recnext_a0_224_nparams"] = np.array(sum(p.numel() for p in net.parameters()))
+    d["recnext_a0_keys"] = np.array(sorted(net.state_dict().keys()))
+    d["torch_version"] = np.array(torch.__version__)
+    np.savez_compressed(os.path.join(OUT, "model_logits_a.npz"), **d)
+    print("recnext_a0 logits", d["recnext_a0_224_logits"][0, :4])
+
+
 if __name__ == "__main__":
     main()
+    model_logits_a()

@@ -49,3 +49,62 @@ class RefRecConv2d(nn.Module):
         has_b = self.down.bias is not None
         return recconv_reference(x, self.down.weight, [c.weight for c in self.convs], self.down.bias if has_b else None,
                                  [c.bias for c in self.convs] if has_b else None, self.mode)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# A-series token mixer (reference model/recattn.py:8-111) restated with the same ATen ops — the CPU baseline of
+# bench.py --model recnext_a3 and a second checker for tests.  Pinned against tests/golden/recattn_*.npz.
+# ---------------------------------------------------------------------------------------------------------
+class RefConvNorm(nn.Sequential):
+    def __init__(self, cin, cout, kernel_size=1, stride=1, padding=0, groups=1):
+        super().__init__()
+        self.add_module("conv", nn.Conv2d(cin, cout, kernel_size, stride, padding, 1, groups, bias=False))
+        self.add_module("norm", nn.BatchNorm2d(cout))
+
+    @torch.no_grad()
+    def fuse(self):
+        w = self.norm.weight / (self.norm.running_var + self.norm.eps) ** 0.5
+        b = self.norm.bias - w * self.norm.running_mean
+        w = w[:, None, None, None] * self.conv.weight
+        c = self.conv
+        m = nn.Conv2d(w.size(1) * c.groups, w.size(0), w.shape[2:], stride=c.stride, padding=c.padding, groups=c.groups)
+        m.weight.data.copy_(w)
+        m.bias.data.copy_(b)
+        return m
+
+
+class RefLinearAttention(nn.Module):
+    def __init__(self, dim, num_heads, quadratic):
+        super().__init__()
+        self.num_heads, self.head_dim, self.quadratic = num_heads, dim // num_heads, quadratic
+        self.qk = RefConvNorm(dim, dim * 2, 1, groups=2)
+        self.pe = RefConvNorm(dim, dim, 3, padding=1, groups=dim)
+
+    def forward(self, x):
+        b, c, h, w = x.shape
+        n = h * w
+        s = n ** -0.5
+        qk = F.elu(self.qk(x)) + 1.0
+        (q, k), v = qk.view(b, 2, self.num_heads, self.head_dim, n).unbind(dim=1), x
+        vt = v.view(b, self.num_heads, self.head_dim, n).transpose(-1, -2) * s
+        if self.quadratic:  # LinearAttention2, model/recattn.py:39-51
+            a = q.transpose(-1, -2) @ k
+            a = a / (a.mean(dim=-1, keepdim=True) + 1e-6)
+            out = (a * s) @ vt
+        else:               # LinearAttention1, model/recattn.py:16-28
+            q_t = q.transpose(-1, -2)
+            out = q_t @ ((k * s) @ vt) / (q_t @ k.mean(dim=-1, keepdim=True) + 1e-6)
+        return out.transpose(-1, -2).reshape(b, c, h, w) + self.pe(v)
+
+
+class RefRecAttn2d(nn.Module):
+    """Same constructor / state_dict as the reference RecAttn2d (model/recattn.py:54-67); forward = ATen ops."""
+
+    def __init__(self, dim, num_heads, kernel_size=5, stage=1, mode="nearest"):
+        super().__init__()
+        self.mode = mode
+        self.down = nn.Sequential(RefConvNorm(dim, dim, kernel_size, 2, kernel_size // 2, dim), RefLinearAttention(dim, num_heads, stage >= 3))
+        self.conv = RefConvNorm(dim, dim, kernel_size, 1, kernel_size // 2, dim)
+
+    def forward(self, x):
+        return self.conv(x + F.interpolate(self.down(x), size=x.shape[2:], mode=self.mode))

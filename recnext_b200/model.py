@@ -16,6 +16,7 @@ from typing import Callable, Sequence
 import torch
 import torch.nn as nn
 
+from .recattn import RecAttn2d
 from .recconv import RecConv2d
 
 VARIANTS = {  # reference model/recnext.py:369-406
@@ -25,6 +26,13 @@ VARIANTS = {  # reference model/recnext.py:369-406
     "recnext_m3": dict(embed_dim=(64, 128, 256, 512), depth=(3, 3, 13, 2)),
     "recnext_m4": dict(embed_dim=(64, 128, 256, 512), depth=(5, 5, 25, 4)),
     "recnext_m5": dict(embed_dim=(80, 160, 320, 640), depth=(7, 7, 35, 2)),
+    # A-series (linear attention + nearest interpolation), reference model/recattn.py:380-426
+    "recnext_a0": dict(series="a", embed_dim=(40, 80, 160, 320), depth=(2, 2, 9, 1)),
+    "recnext_a1": dict(series="a", embed_dim=(48, 96, 192, 384), depth=(3, 3, 15, 2)),
+    "recnext_a2": dict(series="a", embed_dim=(56, 112, 224, 448), depth=(3, 3, 15, 2)),
+    "recnext_a3": dict(series="a", embed_dim=(64, 128, 256, 512), depth=(3, 3, 13, 2), mlp_ratio=1.875),
+    "recnext_a4": dict(series="a", embed_dim=(64, 128, 256, 512), depth=(5, 5, 25, 4), mlp_ratio=1.875),
+    "recnext_a5": dict(series="a", embed_dim=(80, 160, 320, 640), depth=(7, 7, 35, 2), mlp_ratio=1.875),
 }
 
 
@@ -137,6 +145,20 @@ class MetaNeXtBlock(nn.Module):
         return x + self.drop_path(self.channel_mixer(self.norm(self.token_mixer(x))))
 
 
+class MetaNeXtBlockA(nn.Module):
+    """A-series block: x + drop_path(channel_mixer(token_mixer(x))), token_mixer = RecAttn2d(dim, heads = 2^(stage+1))
+    (reference model/recattn.py:162-171; no BatchNorm between the mixers)."""
+
+    def __init__(self, dim, mlp_ratio, act_layer=nn.GELU, stage=0, drop_path=0.0, token_mixer: Callable = RecAttn2d):
+        super().__init__()
+        self.token_mixer = token_mixer(dim, num_heads=2 ** (stage + 1), stage=stage)
+        self.channel_mixer = mlp(dim, dim * mlp_ratio, act_layer)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+
+    def forward(self, x):
+        return x + self.drop_path(self.channel_mixer(self.token_mixer(x)))
+
+
 class Downsample(nn.Module):
     def __init__(self, dim, mlp_ratio, act_layer=nn.GELU):
         super().__init__()
@@ -175,10 +197,11 @@ class RecNextClassifier(nn.Module):
 
 
 class RecNextStage(nn.Module):
-    def __init__(self, cin, cout, depth, mlp_ratio, act_layer, downsample, stage, drop_path, token_mixer):
+    def __init__(self, cin, cout, depth, mlp_ratio, act_layer, downsample, stage, drop_path, token_mixer, series="m"):
         super().__init__()
         self.downsample = Downsample(cin, mlp_ratio, act_layer) if downsample else nn.Identity()
-        self.blocks = nn.Sequential(*[MetaNeXtBlock(cout, mlp_ratio, act_layer, stage, drop_path, token_mixer) for _ in range(depth)])
+        block = MetaNeXtBlockA if series == "a" else MetaNeXtBlock
+        self.blocks = nn.Sequential(*[block(cout, mlp_ratio, act_layer, stage, drop_path, token_mixer) for _ in range(depth)])
 
     def forward(self, x):
         return self.blocks(self.downsample(x))
@@ -186,13 +209,14 @@ class RecNextStage(nn.Module):
 
 class RecNext(nn.Module):
     def __init__(self, in_chans=3, embed_dim: Sequence[int] = (48,), depth: Sequence[int] = (2,), mlp_ratio=2, num_classes=1000,
-                 act_layer=nn.GELU, distillation=False, drop_rate=0.0, drop_path=0.0, token_mixer: Callable = RecConv2d):
+                 act_layer=nn.GELU, distillation=False, drop_rate=0.0, drop_path=0.0, token_mixer: Callable = RecConv2d, series="m"):
         super().__init__()
+        self.series = series
         self.embed_dim, self.num_classes, self.num_features = tuple(embed_dim), num_classes, embed_dim[-1]
         self.stem = RecNextStem(in_chans, embed_dim[0], act_layer)
         stages, cin = [], embed_dim[0]
         for i, (dim, d) in enumerate(zip(embed_dim, depth)):
-            stages.append(RecNextStage(cin, dim, d, mlp_ratio, act_layer, i != 0, i, drop_path, token_mixer))
+            stages.append(RecNextStage(cin, dim, d, mlp_ratio, act_layer, i != 0, i, drop_path, token_mixer, series))
             cin = dim
         self.stages = nn.Sequential(*stages)
         self.head_drop = nn.Dropout(drop_rate)
@@ -225,14 +249,17 @@ def replace_batchnorm(net: nn.Module) -> nn.Module:
     return net
 
 
-def create_model(variant: str, token_mixer: Callable = RecConv2d, **kwargs) -> RecNext:
-    """``create_model('recnext_m3')`` — the timm entry point the reference registers (model/recnext.py:365-407)."""
+def create_model(variant: str, token_mixer: Callable = None, **kwargs) -> RecNext:
+    """``create_model('recnext_m3')`` / ``create_model('recnext_a3')`` — the timm entry points the reference registers
+    (model/recnext.py:365-407, model/recattn.py:380-426)."""
     if variant not in VARIANTS:
         raise ValueError(f"unknown variant {variant!r}; available: {sorted(VARIANTS)}")
     args = dict(VARIANTS[variant])
-    if variant in ("recnext_m4", "recnext_m5") and not kwargs.get("distillation", False):
-        args["drop_path"] = 0.2 if variant == "recnext_m4" else 0.3
+    if variant[-2:] in ("m4", "m5", "a4", "a5") and not kwargs.get("distillation", False):
+        args["drop_path"] = 0.2 if variant.endswith("4") else 0.3
     args.update(kwargs)
+    if token_mixer is None:
+        token_mixer = RecAttn2d if args.get("series", "m") == "a" else RecConv2d
     return RecNext(token_mixer=token_mixer, **args)
 
 

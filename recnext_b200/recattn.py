@@ -25,6 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _native as N
+from . import recconv as _rc
 from .recconv import _DTYPES, _MODES, _stream
 
 
@@ -37,6 +38,23 @@ def _call_desc(x: torch.Tensor, mode: str, wdtype: torch.dtype, has_bias: bool) 
         raise TypeError(f"RecAttn2d kernels are built for 16-bit activations (bfloat16 / float16), got {x.dtype}")
     B, C, H, W = x.shape
     return N.RecConvDesc(B, C, H, W, 5, 1, _MODES[mode], _DTYPES[x.dtype], _DTYPES[wdtype], int(has_bias))
+
+
+def _timing_start():
+    """bench.py's per-launch timing (recconv.timing_begin/end): CUDA events on the launching stream"""
+    if _rc._timing is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _timing_stop(ev0, alg_bytes, shape):
+    if ev0 is None or _rc._timing is None:
+        return
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev1.record()
+    _rc._timing.append((ev0, ev1, alg_bytes, shape))
 
 
 def _prep(x, w, b):
@@ -57,8 +75,10 @@ def recattn_down_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Ten
     B, C, H, W = x.shape
     out = torch.empty(B, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1, device=x.device, dtype=x.dtype)
     with torch.cuda.device(x.device):
+        ev = _timing_start()
         N.check(N.lib().recattn_down_forward(ctypes.byref(d), w.data_ptr(), None if b is None else b.data_ptr(), x.data_ptr(),
                                              out.data_ptr(), _stream(x)), "recattn_down_forward")
+        _timing_stop(ev, (x.numel() + out.numel()) * x.element_size(), ("down",) + tuple(x.shape))
     return out
 
 
@@ -72,8 +92,10 @@ def recattn_up_forward(x: torch.Tensor, z: torch.Tensor, w: torch.Tensor, b: Opt
     w, b = _prep(x, w, b)
     y = torch.empty_like(x)
     with torch.cuda.device(x.device):
+        ev = _timing_start()
         N.check(N.lib().recattn_up_forward(ctypes.byref(d), w.data_ptr(), None if b is None else b.data_ptr(), x.data_ptr(), z.data_ptr(),
                                            int(z.shape[2]), int(z.shape[3]), y.data_ptr(), _stream(x)), "recattn_up_forward")
+        _timing_stop(ev, (2 * x.numel() + z.numel()) * x.element_size(), ("up",) + tuple(x.shape))
     return y
 
 

@@ -99,3 +99,35 @@ def test_model_training_step_gradients_gpu():
         if e > worst:
             worst, worst_name = e, n
     assert worst < 2e-3, (worst, worst_name)
+
+
+# ---- A-series (RecAttn2d token mixers; reference model/recattn.py) -------------------------------------------------
+ZA = np.load(os.path.join(GOLDEN, "model_logits_a.npz"))
+
+
+def test_a_series_state_dict_keys_match_reference():
+    from recnext_b200.model import create_model, replace_batchnorm
+
+    net = create_model("recnext_a0")
+    assert sorted(net.state_dict().keys()) == [str(k) for k in ZA["recnext_a0_keys"]]
+    assert sum(p.numel() for p in net.parameters()) == int(ZA["recnext_a0_224_nparams"])
+    replace_batchnorm(net.eval())  # every ConvNorm / NormLinear folds: the A-series has no un-fusable BatchNorm (besides Downsample.norm)
+    assert sum(isinstance(m, torch.nn.BatchNorm2d) for m in net.modules()) == 3
+
+
+@pytest.mark.gpu
+def test_a_series_full_model_logits_gpu():
+    """RecNeXt-A0 inference (bf16 autocast, BatchNorm folded) with the CUDA RecAttn2d pieces vs the reference's fp32 logits."""
+    from recnext_b200.model import create_model, replace_batchnorm
+
+    net = create_model("recnext_a0").eval()
+    fill_state_dict_(net, seed=0)
+    net.cuda()
+    x = _inputs(224).cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y = net(x).float().cpu().numpy()
+    assert rel_err(y, ZA["recnext_a0_224_logits"]) < 5e-2   # ~40 bf16 layers deep; per-op bar is 2e-2 (tests/test_recattn.py)
+    replace_batchnorm(net)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = net(x).float().cpu().numpy()
+    assert rel_err(y2, ZA["recnext_a0_224_logits"]) < 5e-2

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle.torch_ref import RefRecConv2d, recconv_reference
-from tests.helpers import TOL_FP32, load_recconv_golden, recconv_golden_files, rel_err
+from tests.helpers import GOLDEN, TOL_FP32, load_recconv_golden, recconv_golden_files, rel_err
 
 
 @pytest.mark.parametrize("path", recconv_golden_files(), ids=lambda p: os.path.basename(p)[8:-4])
@@ -30,3 +30,22 @@ def test_ref_module_state_dict_layout():
     keys = list(m.state_dict().keys())
     assert keys == ["down.weight", "down.bias"] + [f"convs.{j}.{n}" for j in range(4) for n in ("weight", "bias")]
     assert tuple(m.down.weight.shape) == (8, 1, 5, 5)
+
+
+def test_ref_recattn_matches_reference_fixtures():
+    """oracle.torch_ref.RefRecAttn2d (the CPU baseline of bench.py --model recnext_a3) against outputs of the
+    unmodified reference RecAttn2d (tests/golden/recattn_*.npz, oracle/gen_golden_recattn.py)."""
+    import glob
+
+    from oracle.torch_ref import RefRecAttn2d
+
+    files = sorted(glob.glob(os.path.join(GOLDEN, "recattn_*.npz")))
+    assert files
+    for p in files:
+        z = np.load(p)
+        B, dim, heads, H, W, stage, mode = (int(v) for v in z["meta"])
+        m = RefRecAttn2d(dim, heads, stage=stage, mode=["bilinear", "nearest"][mode])
+        m.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd:")}, strict=True)
+        with torch.no_grad():
+            y = m.eval()(torch.from_numpy(z["x"])).numpy()
+        assert rel_err(y, z["y"]) < 1e-6
