@@ -199,7 +199,7 @@ struct MTeam {
         b.pitchB = lv.pitchB; b.H = lv.H; b.W = lv.W;
         return b;
     }
-    __device__ __forceinline__ uint32_t tbuf(int g) const { return tsm32 + (uint32_t)(pl.off_upper + g * pl.upper_bytes + pl.offT); }
+    __device__ __forceinline__ uint32_t tbuf(int g, int l) const { return tsm32 + (uint32_t)(pl.off_upper + g * pl.upper_bytes + pl.lv[l].offT); }
     __device__ __forceinline__ uint32_t frag(int g, int reg0) const { return smem32 + (uint32_t)(pl.smFrag + ((g * pl.nregs + reg0) * 32 + lane) * 4); }
     __device__ __forceinline__ float bias(int g, int slot) const {
         float v = 0.f;
@@ -299,7 +299,7 @@ __device__ __forceinline__ void m_load_z(const MTeam<T>& tm, const T* __restrict
     const int j = tm.tl & (LW - 1), rg = tm.tl >> tm.rt.z_shift;
     const unsigned short* z16 = reinterpret_cast<const unsigned short*>(z);
     for (int g = 0; g < pl.G; ++g) {
-        const uint32_t Tb = tm.tbuf(g);
+        const uint32_t Tb = tm.tbuf(g, 1);
         for (int i = rg; i < lz.H; i += RG) {
             const uint32_t trow = Tb + (uint32_t)(i * lz.tpB) + 4u;
             const unsigned short* srow = z16 + ((long)g * lz.H + i) * lz.W;
@@ -335,7 +335,7 @@ __device__ __forceinline__ void m_up_add(const MTeam<T>& tm, unsigned char* smem
         const float lx0 = tx0.lam, lx1 = tx1.lam, hx0 = 1.f - lx0, hx1 = 1.f - lx1;
         for (int g = 0; g < pl.G; ++g) {
             const MBuf b = tm.buf(g, l - 1);
-            const uint32_t Tb = tm.tbuf(g);
+            const uint32_t Tb = tm.tbuf(g, l);
             for (int i = rg; i < ld.H; i += RG) {
                 const IdxLam ty = ytab[i];
                 const uint32_t t0 = Tb + (uint32_t)ty.i0 * ls.tpB;
@@ -378,7 +378,7 @@ __device__ __forceinline__ void m_up2x_add(const MTeam<T>& tm, int l) {
     for (int a = j; a < Ws; a += LW) {
         for (int g = 0; g < pl.G; ++g) {
             const MBuf b = tm.buf(g, l - 1);
-            const uint32_t Tc = tm.tbuf(g) + 2u * (a + 1);   // element a - 1 (interior at 2)
+            const uint32_t Tc = tm.tbuf(g, l) + 2u * (a + 1);   // element a - 1 (interior at 2)
             auto hrow = [&](uint32_t p, float& h0, float& h1) {
                 const float ta = MmaT<T>::one(m_lds16(p)), tb = MmaT<T>::one(m_lds16(p + 2)), tc = MmaT<T>::one(m_lds16(p + 4));
                 const float q = 0.75f * tb;
@@ -429,6 +429,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
         for (int i = tid; i < n16; i += blockDim.x) z[i] = zero;
 #pragma unroll
         for (int l = 1; l <= L; ++l) {
+            if (pl.lv[l].tabY < 0) continue;
             rc_build_fwd_table(reinterpret_cast<IdxLam*>(smem + pl.smTab + pl.lv[l].tabY), pl.lv[l].H, pl.lv[l - 1].H, pl.mode, tid, blockDim.x);
             rc_build_fwd_table(reinterpret_cast<IdxLam*>(smem + pl.smTab + pl.lv[l].tabX), pl.lv[l].W, pl.lv[l - 1].W, pl.mode, tid, blockDim.x);
         }
@@ -476,17 +477,18 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                     if (nxt < end) issue_load(nxt);
                 } else if (variant == 2) {
                     // level 1 is not materialised; T is filled below
-                } else {
-                    // the raw batch landed on top of levels >= 1: restore their zero borders
-                    const uint4 zero = {0u, 0u, 0u, 0u};
-                    for (int g = 0; g < G; ++g) {
-                        uint4* z = reinterpret_cast<uint4*>(raw + g * pl.upper_bytes);
-                        for (int i = tm.tl; i < pl.zero_bytes / 16; i += pl.team_lanes) z[i] = zero;
-                    }
-                    tm.sync();
                 }
             } else {
                 m_repack<T>(tm, gx + p0);
+                tm.sync();
+            }
+            if (variant == 0 && (rt.use_tma ? L > 0 : L > 1)) {
+                // the raw batch and the T buffers of the previous batch landed on top of levels >= 1: restore their zero borders
+                const uint4 zero = {0u, 0u, 0u, 0u};
+                for (int g = 0; g < G; ++g) {
+                    uint4* z = reinterpret_cast<uint4*>(raw + g * pl.upper_bytes);
+                    for (int i = tm.tl; i < pl.zero_bytes / 16; i += pl.team_lanes) z[i] = zero;
+                }
                 tm.sync();
             }
             // ---- down chain: x_l = down(x_{l-1})   (model/recnext.py:27-29)
@@ -525,7 +527,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                 m_load_z<T>(tm, reinterpret_cast<const T*>(a.gy) + pidx * (long)(pl.lv[1].H * pl.lv[1].W));
                 tm.sync();
                 const MLevel& lv = pl.lv[1];
-                if (lv.exact2x && pl.mode == 0 && !(rt.dbg & 1)) m_up2x_add<T>(tm, 1);
+                if (lv.tabY < 0) m_up2x_add<T>(tm, 1);
                 else m_up_add<T>(tm, smem, 1);
                 tm.sync();
             }
@@ -562,7 +564,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                     const int i0 = mt * 16, Wl = lv.W;
                     const int ia = i0 + 2 * lg;
                     const bool va = ia < lv.H, vb = ia + 1 < lv.H;
-                    const uint32_t ta = tm.tbuf(g) + (uint32_t)(ia * lv.tpB) + 4u + 4u * lt, tpB = (uint32_t)lv.tpB;
+                    const uint32_t ta = tm.tbuf(g, l) + (uint32_t)(ia * lv.tpB) + 4u + 4u * lt, tpB = (uint32_t)lv.tpB;
                     m_conv_rows<T, false>(in, lv.ntc, i0, lv.NT, tm.frag(g, 20 + 10 * (L - l)), tm.bias(g, 1 + (L - l)), lane,
                                           [&](int q, const float (&acc)[4]) {
                         const int c = 8 * q + 2 * lt;
@@ -582,7 +584,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                     });
                 }
                 tm.sync();
-                if (lv.exact2x && pl.mode == 0 && !(rt.dbg & 1)) m_up2x_add<T>(tm, l);
+                if (lv.tabY < 0) m_up2x_add<T>(tm, l);
                 else m_up_add<T>(tm, smem, l);
                 tm.sync();
             }

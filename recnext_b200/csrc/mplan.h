@@ -31,7 +31,10 @@ struct MLevel {
     int pitchB;          // row pitch in bytes (odd multiple of 16)
     int off, parDelta;   // byte offset of the even-row array inside a plane block; distance to the odd-row array
     int tpB;             // l >= 1: row pitch (bytes) of the T buffer of this level; interior at element 2
-    int tabY, tabX;      // l >= 1: byte offsets (table region) of IdxLam[H_{l-1}] / IdxLam[W_{l-1}]
+    int offT;            // l >= 1: byte offset (upper block) of T_l.  T_l is written when every level deeper than l is dead,
+                         // so it starts where level l+1 starts (the zero borders it tramples are restored per batch)
+    int tabY, tabX;      // l >= 1: byte offsets (table region) of IdxLam[H_{l-1}] / IdxLam[W_{l-1}]; -1 if the level takes
+                         // the fixed-stencil exact-2x bilinear path and needs no table
     int exact2x;         // level l-1 is exactly 2x this level
     int up_shift;        // l >= 1: up-add lane mapping over level l-1: lanes per row group = 1 << up_shift
     int up_rpg;          // l >= 1: exact-2x path: source rows per row group
@@ -49,9 +52,8 @@ struct MPlan {
     MLevel lv[kMaxLevel + 1];
     int l0_bytes;        // level-0 buffer of one plane (the team slice starts with G of them)
     int upper_bytes;     // levels 1..L + T of one plane (MLevel::off of l >= 1 and offT are relative to this block)
-    int zero_bytes;      // leading part of an upper block that holds padded level buffers (re-zeroed per batch when the
-                         // raw batch aliases the upper region)
-    int offT;            // byte offset of the T buffer inside an upper block
+    int zero_bytes;      // leading part of an upper block that holds padded level buffers (re-zeroed per batch: the raw
+                         // batch and the T buffers of shallower levels land on top of it)
     int raw_bytes;       // G raw planes
     int off_upper;       // byte offset (team slice) of the upper region = the TMA landing buffer: a batch is loaded
                          // only after the last use of levels >= 1 and T (under the final conv)
@@ -101,7 +103,7 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
         g.ntc = g.NT <= 1 ? 1 : (g.NT == 2 ? 2 : (g.NT <= 4 ? 4 : 7));
     }
     // level buffers: level 0 on its own, levels >= 1 + T in the "upper" block
-    int off = 0, tmax = 0;
+    int off = 0;
     for (int l = 0; l <= L; ++l) {
         MLevel& g = pl.lv[l];
         int kb = g.NT + 1;                                        // as the input of a stride-1 conv
@@ -119,19 +121,27 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
         g.exact2x = (l >= 1 && pl.lv[l - 1].H == 2 * g.H && pl.lv[l - 1].W == 2 * g.W) ? 1 : 0;
         if (l >= 1) {
             g.tpB = rc_round_up((g.W + 4) * 2, 4);
-            if (g.H * g.tpB > tmax) tmax = g.H * g.tpB;
         }
     }
     pl.zero_bytes = off;
-    pl.offT = off;
-    off += rc_round_up(tmax, 128);
-    pl.upper_bytes = off;
+    {
+        int top = off;
+        for (int l = 1; l <= L; ++l) {
+            MLevel& g = pl.lv[l];
+            g.offT = l < L ? pl.lv[l + 1].off : off;
+            const int e = g.offT + rc_round_up(g.H * g.tpB, 128);
+            if (e > top) top = e;
+        }
+        pl.upper_bytes = top;
+    }
 
-    // tables shared by the CTA
+    // tables shared by the CTA (levels on the generic interpolation path only)
     int tb = 0;
     for (int l = 1; l <= L; ++l) {
-        pl.lv[l].tabY = tb; tb += 8 * pl.lv[l - 1].H;
-        pl.lv[l].tabX = tb; tb += 8 * pl.lv[l - 1].W;
+        MLevel& g = pl.lv[l];
+        if (g.exact2x && mode == 0 && !(opt.dbg & 1)) { g.tabY = -1; g.tabX = -1; continue; }
+        g.tabY = tb; tb += 8 * pl.lv[l - 1].H;
+        g.tabX = tb; tb += 8 * pl.lv[l - 1].W;
     }
     tb = rc_round_up(tb, 128);
 
@@ -186,9 +196,11 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
         pl.lv[l].up_rpg = rc_div_up(pl.lv[l].H, pl.team_lanes >> pl.lv[l].up_shift);
     }
 
+    // persistent grid: one CTA per SM; with less work than team slots, spread it over as many SMs as possible
+    // (a batch is one warp-serial chain of stages: an idle SM is worth more than a full one)
     const long total = (long)pl.n_cg * B;
     long grid = opt.num_sms;
-    if (total < grid * NTEAM) grid = (total + NTEAM - 1) / NTEAM;
+    if (total < grid) grid = total;
     if (grid < 1) grid = 1;
     pl.grid = (int)grid;
     return 0;

@@ -64,6 +64,8 @@ _CASES = [
     (2, 128, 100, 167, 3, "bilinear", True), (2, 256, 50, 84, 2, "bilinear", False), (2, 512, 25, 42, 1, "bilinear", True),
     (1, 7, 25, 21, 3, "bilinear", True), (1, 16, 96, 96, 4, "bilinear", False), (3, 6, 12, 10, 0, "bilinear", True),
     (2, 4, 33, 65, 5, "nearest", False), (1, 2, 10, 300, 2, "bilinear", False),
+    # detection stage 0 (BASELINE configs[4]: 800x1333 -> 200x336 / unpadded 200x334, level 4): one plane per SM, 8 warps
+    (2, 64, 200, 336, 4, "bilinear", False), (1, 8, 200, 334, 4, "bilinear", True),
 ]
 
 

@@ -25,7 +25,8 @@ CASES = [(3, 64, 56, 56, 4, "bilinear", False), (3, 128, 28, 28, 3, "bilinear", 
          (5, 512, 7, 7, 1, "bilinear", False), (2, 80, 56, 56, 4, "nearest", True), (2, 256, 50, 84, 2, "bilinear", False),
          (2, 512, 25, 42, 1, "bilinear", True), (1, 7, 25, 21, 3, "bilinear", True), (1, 1, 1, 1, 2, "bilinear", True),
          (4, 6, 2, 3, 1, "nearest", False), (7, 9, 8, 8, 0, "bilinear", True), (2, 128, 100, 168, 3, "bilinear", False),
-         (2, 128, 100, 167, 3, "bilinear", False), (64, 64, 56, 56, 4, "bilinear", False), (1, 16, 96, 96, 4, "bilinear", False)]
+         (2, 128, 100, 167, 3, "bilinear", False), (64, 64, 56, 56, 4, "bilinear", False), (1, 16, 96, 96, 4, "bilinear", False),
+         (2, 64, 200, 336, 4, "bilinear", False), (1, 8, 200, 334, 4, "bilinear", True), (1, 4, 200, 336, 4, "nearest", False)]
 dev = "cuda"
 rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 bad = 0
@@ -36,6 +37,7 @@ for dt in (torch.bfloat16, torch.float16):
         ws = [torch.empty(C, 1, 5, 5, device=dev).uniform_(-0.2, 0.2) for _ in range(L + 2)]
         bs = [torch.empty(C, device=dev).uniform_(-0.2, 0.2) for _ in range(L + 2)] if bias else None
         desc = R.recconv.plan_describe((B, C, H, W), 5, L, mode, dt, bias, False) if (B, C) == (3, 64) or H >= 96 else ""
+        if dt == torch.float16 and H >= 200: continue
         try:
             y = R.recconv_forward(x, ws, bs, 5, L, mode)
             torch.cuda.synchronize()
