@@ -175,6 +175,17 @@ static int make_mplan(const recconv_desc* d, MPlan& pl) {
     static int force_mma = -1;
     if (force_mma < 0) { const char* e = getenv("RECNEXT_PATH"); force_mma = (e && strcmp(e, "mma") == 0) ? 1 : 0; }
     if (!force_mma && d->H * d->W < 100) return 1;
+    // the specialised (compile-time geometry) kernels of the small stage shapes run 24 warps per SM; anything that does
+    // not match one of them is planned for the generic kernel (16 warps at 128 registers)
+    if (!opt.force_NT && !opt.force_TW) {
+        opt.max_warps = m_static_max_warps(d->H, d->W);
+        if (opt.max_warps > 16) {
+            if (m_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, opt) == 0 &&
+                (pl.threads <= 512 || m_static_geometry(pl)))
+                return 0;
+            opt.max_warps = 16;
+        }
+    }
     return m_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, opt) == 0 ? 0 : 1;
 }
 

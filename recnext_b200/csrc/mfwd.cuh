@@ -93,30 +93,46 @@ struct MBuf {
 // parity array (odd chunk pitch): conflict free.
 // epi(q, acc): acc[0..1] = (row i0 + 2(lane/4), columns 8q + 2(lane%4) + {0,1}), acc[2..3] = same columns of the next row.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void m_ldsm1(uint32_t& r0, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];\n" : "=r"(r0) : "r"(addr));
+}
+
+// row set E_r of an M-tile: the 8 image rows i0 + r + 0, 2, .., 14 (one parity: consecutive rows of one parity array,
+// conflict free), k-blocks q0 .. q0 + NB - 1.  Lane L addresses row 2 (L % 8) of k-block L / 8 of each ldmatrix.
+template <int NB>
+__device__ __forceinline__ void m_load_rowset(uint32_t (&E)[NB], const MBuf& in, int row0, int rowMax, uint32_t colB, int lane) {
+    int rr = row0 + 2 * (lane & 7);
+    rr = rr < rowMax ? rr : rowMax;
+    const uint32_t a = in.row(rr) + colB + (uint32_t)(lane >> 3) * 16u;
+#pragma unroll
+    for (int kb = 0; kb < NB; kb += 4) {
+        if (NB - kb >= 4) m_ldsm4(E[kb], E[kb + 1], E[kb + 2], E[kb + 3], a + (uint32_t)kb * 16u);
+        else if (NB - kb == 3) { m_ldsm2(E[kb], E[kb + 1], a + (uint32_t)kb * 16u); m_ldsm1(E[kb + 2], a - (uint32_t)(lane >> 3) * 16u + (uint32_t)(kb + 2) * 16u); }
+        else if (NB - kb == 2) m_ldsm2(E[kb], E[kb + 1], a + (uint32_t)kb * 16u);
+        else m_ldsm1(E[kb], a - (uint32_t)(lane >> 3) * 16u + (uint32_t)kb * 16u);
+    }
+}
+
 template <typename T, int NTC, bool FULL, class Epi>
 __device__ __forceinline__ void m_conv_s1_tile(const MBuf& in, int i0, int q0, int nt, uint32_t bfr, float bias, int lane, Epi epi) {
     float acc[NTC][4];
 #pragma unroll
     for (int q = 0; q < NTC; ++q) { acc[q][0] = bias; acc[q][1] = bias; acc[q][2] = bias; acc[q][3] = bias; }
-    const int lrow = 2 * (lane & 7) + ((lane >> 3) & 1);
-    const uint32_t lcol = (uint32_t)(q0 + (lane >> 4)) * 16u;
+    // Fragment rows 0..7 are image rows i0 + 0, 2, .., 14 and fragment rows 8..15 are i0 + 1, 3, .., 15.  For filter row r
+    // the A operand is therefore (E_r, E_{r+1}) with E_r = image rows i0 + r + {0, 2, .., 14}: the lower half of one
+    // filter row is the upper half of the previous one, so an M-tile needs 6 row sets instead of 10 (40 % less
+    // shared-memory traffic), each a conflict-free run of consecutive rows of one parity array.
     const int rowMax = in.H + 3;
+    const uint32_t colB = (uint32_t)q0 * 16u;
+    uint32_t E[2][NTC + 1];
+    m_load_rowset<NTC + 1>(E[0], in, i0, rowMax, colB, lane);
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
-        int rr = i0 + lrow + r;
-        rr = rr < rowMax ? rr : rowMax;
-        const uint32_t arow = in.row(rr) + lcol;
-        uint32_t A[NTC + 1][2];
-#pragma unroll
-        for (int kb = 0; kb + 1 <= NTC; kb += 2)
-            if (FULL || q0 + kb <= nt) m_ldsm4(A[kb][0], A[kb][1], A[kb + 1][0], A[kb + 1][1], arow + (uint32_t)kb * 16u);
-        if (((NTC + 1) & 1) != 0) {
-            if (FULL || q0 + NTC <= nt) m_ldsm2(A[NTC][0], A[NTC][1], arow - (uint32_t)(lane >> 4) * 16u + (uint32_t)NTC * 16u);
-        }
+        m_load_rowset<NTC + 1>(E[(r + 1) & 1], in, i0 + r + 1, rowMax, colB, lane);
         const uint32_t b0 = m_lds32(bfr + (2 * r) * 128), b1 = m_lds32(bfr + (2 * r + 1) * 128);
 #pragma unroll
         for (int q = 0; q < NTC; ++q)
-            if (FULL || q0 + q < nt) MmaT<T>::mma16(acc[q], A[q][0], A[q][1], A[q + 1][0], A[q + 1][1], b0, b1);
+            if (FULL || q0 + q < nt) MmaT<T>::mma16(acc[q], E[r & 1][q], E[(r + 1) & 1][q], E[r & 1][q + 1], E[(r + 1) & 1][q + 1], b0, b1);
     }
 #pragma unroll
     for (int q = 0; q < NTC; ++q)
@@ -637,7 +653,7 @@ __global__ void __launch_bounds__(512, 1) recconv_mfwd_kernel(const __grid_const
 }
 // specialised kernel: plane geometry (H0 x W0, L0 levels, G0 planes per batch) fixed at compile time
 template <typename T, int H0, int W0, int L0, int G0>
-__global__ void __launch_bounds__(512, 1) recconv_mfwd_static_kernel(const __grid_constant__ MPlan rt, const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(32 * m_static_max_warps(H0, W0), 1) recconv_mfwd_static_kernel(const __grid_constant__ MPlan rt, const __grid_constant__ KernelArgs a) {
     constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1);
     m_fwd_body<T, L0>(sp, rt, a);
 }
@@ -688,6 +704,7 @@ inline cudaError_t m_launch_fwd_t(const MPlan& pl, const KernelArgs& a, cudaStre
         if (err != cudaSuccess) return err;
         configured = 1;
     }
+    if (pl.threads > 512) return cudaErrorInvalidConfiguration;  // planned for a specialised kernel that did not match
     recconv_mfwd_kernel<T><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
     return cudaGetLastError();
 }

@@ -120,7 +120,10 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
         if (l == 0) { pl.l0_bytes = off; off = 0; }
         g.exact2x = (l >= 1 && pl.lv[l - 1].H == 2 * g.H && pl.lv[l - 1].W == 2 * g.W) ? 1 : 0;
         if (l >= 1) {
+            // T rows are written from MMA fragments (8 rows two apart x 4 words per store): a pitch of 8 (mod 64) bytes puts
+            // those 32 words in 32 different banks
             g.tpB = rc_round_up((g.W + 4) * 2, 4);
+            while ((g.tpB & 63) != 8) g.tpB += 4;
         }
     }
     pl.zero_bytes = off;
@@ -174,7 +177,7 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
     const long avail = (long)opt.smem_limit - pl.smTeams;
     if (avail < pl.team_bytes) return 1;
     const int fit = (int)(avail / pl.team_bytes);
-    int max_warps = opt.max_warps > 16 ? 16 : opt.max_warps;
+    int max_warps = opt.max_warps > 24 ? 24 : opt.max_warps;   // 16: any kernel (128 registers); 24: the small-plane specialised kernels
     if (max_warps < 1) max_warps = 1;
     int TW = 1;
     if (opt.force_TW) TW = opt.force_TW;
@@ -183,7 +186,7 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
     if (NTEAM * TW > max_warps) NTEAM = max_warps / TW;
     if (TW > 1 && NTEAM > 15) NTEAM = 15;   // one named barrier per team
     if (opt.force_NT) NTEAM = opt.force_NT;
-    if (NTEAM < 1 || NTEAM > fit || NTEAM * TW > 16 || NTEAM > 16) return 1;
+    if (NTEAM < 1 || NTEAM > fit || NTEAM * TW > max_warps || NTEAM > 24) return 1;
     pl.TW = TW; pl.NTEAM = NTEAM; pl.team_lanes = 32 * TW; pl.threads = 32 * TW * NTEAM;
     pl.smem_bytes = pl.smTeams + NTEAM * pl.team_bytes;
     if (pl.smem_bytes > opt.smem_limit) return 1;
@@ -206,6 +209,10 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
     return 0;
 }
 
+// warps per SM of the specialised kernels: planes up to 28x28 need <= 80 registers per thread (ptxas), so 24 warps fit
+// (measured: 24 warps buy nothing — the kernels are bound by shared-memory bandwidth, not latency — so this stays at 16)
+RC_HD constexpr int m_static_max_warps(int H, int W) { return (H <= 0 && W <= 0) ? 24 : 16; }
+
 // The layout-defining part of a plan for fixed plane geometry, evaluated at COMPILE time by the specialised kernels
 // (mfwd.cuh): every level size, pitch and offset folds into immediates.  The host compares it field by field with
 // the run-time plan before choosing a specialised kernel; B, C, grid, bias, parameter dtype and TMA eligibility
@@ -214,6 +221,7 @@ RC_HD constexpr MPlan m_static_plan(int H, int W, int L, int G, int dtype) {
     MPlan pl{};
     MPlanOptions o{};
     o.force_G = G;
+    o.max_warps = m_static_max_warps(H, W);
     m_make_plan(pl, 1, G, H, W, 5, L, 0, dtype, dtype, 0, o);
     return pl;
 }
