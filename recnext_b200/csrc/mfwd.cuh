@@ -421,6 +421,140 @@ __device__ __forceinline__ void m_up2x_add(const MTeam<T>& tm, int l) {
     }
 }
 
+// The same with TWO source columns (a, a+1; a even) per lane: three aligned 32-bit loads of T feed four destination
+// columns, and the loop / address overhead is paid once per eight outputs.  Same arithmetic per output as above
+// (bit-identical).  RECNEXT_MDBG=4; measured 8 % SLOWER at stage 0 (0.157 vs 0.145 ms): the two row groups a warp then
+// needs collide in the banks — kept as a checked alternative (tools/ab_upsample.py).
+template <typename T>
+__device__ __forceinline__ void m_up2x_add2(const MTeam<T>& tm, int l) {
+    const MPlan& pl = tm.pl;
+    const MLevel& ls = pl.lv[l];
+    const MLevel& ld = pl.lv[l - 1];
+    const int LW = 1 << ls.up2_shift;
+    const int j = tm.tl & (LW - 1), rg = tm.tl >> ls.up2_shift;
+    const int Hs = ls.H, Ws = ls.W, Wd = ld.W;
+    const int rpg = ls.up2_rpg;
+    const int m0 = rg * rpg, m1 = (m0 + rpg) < Hs ? (m0 + rpg) : Hs;
+    if (m0 >= m1) return;
+    const uint32_t tpB = (uint32_t)ls.tpB;
+    for (int a = 2 * j; a < Ws; a += 2 * LW) {
+        const bool second = 2 * a + 2 < Wd;   // destination columns 2a+2, 2a+3 exist (source column a+1 < Ws)
+        for (int g = 0; g < pl.G; ++g) {
+            const MBuf b = tm.buf(g, l - 1);
+            const uint32_t Tc = tm.tbuf(g, l) + 2u * a;   // elements a, a+1 = source columns a-2, a-1 (interior at 2)
+            auto hrow = [&](uint32_t p, float (&h)[4]) {
+                const uint32_t w0 = m_lds32(p), w1 = m_lds32(p + 4), w2 = m_lds32(p + 8);
+                const float tm1 = MmaT<T>::unpack(w0).y;
+                const float2 t01 = MmaT<T>::unpack(w1);
+                const float tp2 = MmaT<T>::lo(w2);
+                const float qa = 0.75f * t01.x, qb = 0.75f * t01.y;
+                h[0] = fmaf(0.25f, tm1, qa);
+                h[1] = fmaf(0.25f, t01.y, qa);
+                h[2] = fmaf(0.25f, t01.x, qb);
+                h[3] = fmaf(0.25f, tp2, qb);
+            };
+            float hp[4], hc[4], hn[4];
+            hrow(Tc + (uint32_t)(m0 > 0 ? m0 - 1 : 0) * tpB, hp);
+            uint32_t tp = Tc + (uint32_t)m0 * tpB;
+            hrow(tp, hc);
+            uint32_t d0 = b.row(2 * m0 + 2) + 4u + 4u * a, d1 = b.row(2 * m0 + 3) + 4u + 4u * a;
+            for (int m = m0; m < m1; ++m) {
+                if (m + 1 < Hs) tp += tpB;
+                hrow(tp, hn);
+                float q[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) q[c] = 0.75f * hc[c];
+                m_sts32(d0, MmaT<T>::add2(m_lds32(d0), MmaT<T>::pack(fmaf(0.25f, hp[0], q[0]), fmaf(0.25f, hp[1], q[1]))));
+                m_sts32(d1, MmaT<T>::add2(m_lds32(d1), MmaT<T>::pack(fmaf(0.25f, hn[0], q[0]), fmaf(0.25f, hn[1], q[1]))));
+                if (second) {
+                    m_sts32(d0 + 4u, MmaT<T>::add2(m_lds32(d0 + 4u), MmaT<T>::pack(fmaf(0.25f, hp[2], q[2]), fmaf(0.25f, hp[3], q[3]))));
+                    m_sts32(d1 + 4u, MmaT<T>::add2(m_lds32(d1 + 4u), MmaT<T>::pack(fmaf(0.25f, hn[2], q[2]), fmaf(0.25f, hn[3], q[3]))));
+                }
+                d0 += (uint32_t)b.pitchB; d1 += (uint32_t)b.pitchB;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { hp[c] = hc[c]; hc[c] = hn[c]; }
+            }
+        }
+    }
+}
+
+// Exact-2x bilinear upsample + add on the tensor cores (RECNEXT_MDBG=8; measured 5 % slower than the CUDA-core version
+// above because its fragment-shaped read-modify-write is two-way bank conflicted — kept as a checked alternative).  The horizontal pass is one MMA per (16 source rows, 8
+// destination columns): P[m, J] = sum_n T[m, n] * Ux[J, n] with A = 16 rows x 16 elements of T (ldmatrix) and B = the
+// constant 0.25 / 0.75 band (exact in bf16; products exact, fp32 sums of two terms: P is the exact fp32 result).
+// Fragment row g is source row m0 - 1 + 2g and fragment row g + 8 is m0 + 2g, so a thread holds two vertically
+// adjacent source rows and gets the other two neighbours from lanes g -+ 1 with one shuffle each; the vertical
+// 0.25 / 0.75 combination, the rounding and the `x + u` read-modify-write stay in fp32 / packed bf16 on the CUDA
+// cores.  An M-tile yields the 14 source rows m0 .. m0 + 13 (28 destination rows); rows and the replicate border
+// columns kept in T implement ATen's index clamping.  Same operation order as m_up2x_add: bit-identical results.
+template <typename T>
+__device__ __forceinline__ void m_up2x_mma(const MTeam<T>& tm, int l) {
+    const MPlan& pl = tm.pl;
+    const MLevel& ls = pl.lv[l];
+    const MLevel& ld = pl.lv[l - 1];
+    const int lane = tm.lane, g8 = lane >> 2, t4 = lane & 3;
+    const int Hs = ls.H, Wd = ld.W;
+    const int NTd = ld.NT;                     // destination n-tiles (8 columns)
+    const int MTs = (Hs + 13) / 14;            // source M-tiles of 14 rows
+    // constant B fragments: destination column j of an n-tile (0..7), window element k (0..15); q even / odd
+    uint32_t Bc[2][2];
+#pragma unroll
+    for (int par = 0; par < 2; ++par)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 2 * t4 + 8 * h + e - 4 * par, j = g8, a = j >> 1;
+                v[e] = (j & 1) ? (k == a + 2 ? 0.75f : (k == a + 3 ? 0.25f : 0.f)) : (k == a + 1 ? 0.25f : (k == a + 2 ? 0.75f : 0.f));
+            }
+            Bc[par][h] = MmaT<T>::pack(v[0], v[1]);
+        }
+    const int frow = 2 * (lane & 7) + ((lane >> 3) & 1) - 1;   // source row offset of this lane's ldmatrix address
+    for (int g = 0, mt = tm.wt; g < pl.G; mt += pl.TW) {
+        if (mt >= MTs) { mt -= MTs + pl.TW; ++g; continue; }
+        const MBuf b = tm.buf(g, l - 1);
+        const int m0 = 14 * mt;
+        int rr = m0 + frow;
+        rr = rr < 0 ? 0 : (rr > Hs - 1 ? Hs - 1 : rr);
+        const uint32_t arow = tm.tbuf(g, l) + (uint32_t)(rr * ls.tpB) + (uint32_t)(lane >> 4) * 16u;
+        const int r0 = m0 - 1 + 2 * g8, r1 = r0 + 1;             // the two source rows of this thread
+        const bool v0 = g8 >= 1 && r0 < Hs, v1 = g8 <= 6 && r1 < Hs;
+        const uint32_t d00 = b.row(2 * r0 + 2) + 4u + 4u * t4, d01 = b.row(2 * r0 + 3) + 4u + 4u * t4;
+        const uint32_t d10 = b.row(2 * r1 + 2) + 4u + 4u * t4, d11 = b.row(2 * r1 + 3) + 4u + 4u * t4;
+        for (int p = 0; 2 * p < NTd; ++p) {
+            uint32_t a0, a1, a2, a3;
+            m_ldsm4(a0, a1, a2, a3, arow + (uint32_t)p * 16u);
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                const int q = 2 * p + par;
+                if (q < NTd) {
+                    float P[4] = {0.f, 0.f, 0.f, 0.f};
+                    MmaT<T>::mma16(P, a0, a1, a2, a3, Bc[par][0], Bc[par][1]);
+                    const float up0 = __shfl_up_sync(0xffffffffu, P[2], 4), up1 = __shfl_up_sync(0xffffffffu, P[3], 4);
+                    const float dn0 = __shfl_down_sync(0xffffffffu, P[0], 4), dn1 = __shfl_down_sync(0xffffffffu, P[1], 4);
+                    if (8 * q + 2 * t4 < Wd) {
+                        const uint32_t co = 16u * q;
+                        const float q00 = 0.75f * P[0], q01 = 0.75f * P[1], q10 = 0.75f * P[2], q11 = 0.75f * P[3];
+                        if (v0) {
+                            const uint32_t e = MmaT<T>::pack(fmaf(0.25f, up0, q00), fmaf(0.25f, up1, q01));
+                            const uint32_t f = MmaT<T>::pack(fmaf(0.25f, P[2], q00), fmaf(0.25f, P[3], q01));
+                            m_sts32(d00 + co, MmaT<T>::add2(m_lds32(d00 + co), e));
+                            m_sts32(d01 + co, MmaT<T>::add2(m_lds32(d01 + co), f));
+                        }
+                        if (v1) {
+                            const uint32_t e = MmaT<T>::pack(fmaf(0.25f, P[0], q10), fmaf(0.25f, P[1], q11));
+                            const uint32_t f = MmaT<T>::pack(fmaf(0.25f, dn0, q10), fmaf(0.25f, dn1, q11));
+                            m_sts32(d10 + co, MmaT<T>::add2(m_lds32(d10 + co), e));
+                            m_sts32(d11 + co, MmaT<T>::add2(m_lds32(d11 + co), f));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel body.  pl = layout, rt = run-time fields (the same object in the generic kernel).  LS >= 0: the level
 // count is a compile-time constant and every loop over levels is fully unrolled, so that with a constexpr `pl`
@@ -498,12 +632,12 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                 m_repack<T>(tm, gx + p0);
                 tm.sync();
             }
-            if (variant == 0 && (rt.use_tma ? L > 0 : L > 1)) {
+            if (variant == 0 && L > 0) {
                 // the raw batch and the T buffers of the previous batch landed on top of levels >= 1: restore their zero borders
                 const uint4 zero = {0u, 0u, 0u, 0u};
                 for (int g = 0; g < G; ++g) {
                     uint4* z = reinterpret_cast<uint4*>(raw + g * pl.upper_bytes);
-                    for (int i = tm.tl; i < pl.zero_bytes / 16; i += pl.team_lanes) z[i] = zero;
+                    for (int i = tm.tl; i < pl.upper_bytes / 16; i += pl.team_lanes) z[i] = zero;
                 }
                 tm.sync();
             }
@@ -543,7 +677,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                 m_load_z<T>(tm, reinterpret_cast<const T*>(a.gy) + pidx * (long)(pl.lv[1].H * pl.lv[1].W));
                 tm.sync();
                 const MLevel& lv = pl.lv[1];
-                if (lv.tabY < 0) m_up2x_add<T>(tm, 1);
+                if (lv.tabY < 0) { if (rt.dbg & 4) m_up2x_add2<T>(tm, 1); else if (rt.dbg & 8) m_up2x_mma<T>(tm, 1); else m_up2x_add<T>(tm, 1); }
                 else m_up_add<T>(tm, smem, 1);
                 tm.sync();
             }
@@ -600,7 +734,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
                     });
                 }
                 tm.sync();
-                if (lv.tabY < 0) m_up2x_add<T>(tm, l);
+                if (lv.tabY < 0) { if (rt.dbg & 4) m_up2x_add2<T>(tm, l); else if (rt.dbg & 8) m_up2x_mma<T>(tm, l); else m_up2x_add<T>(tm, l); }
                 else m_up_add<T>(tm, smem, l);
                 tm.sync();
             }

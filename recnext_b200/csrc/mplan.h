@@ -38,6 +38,7 @@ struct MLevel {
     int exact2x;         // level l-1 is exactly 2x this level
     int up_shift;        // l >= 1: up-add lane mapping over level l-1: lanes per row group = 1 << up_shift
     int up_rpg;          // l >= 1: exact-2x path: source rows per row group
+    int up2_shift, up2_rpg;  // l >= 1: exact-2x path with two source columns per lane (the default)
 };
 
 struct MPlan {
@@ -122,8 +123,9 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
         if (l >= 1) {
             // T rows are written from MMA fragments (8 rows two apart x 4 words per store): a pitch of 8 (mod 64) bytes puts
             // those 32 words in 32 different banks
-            g.tpB = rc_round_up((g.W + 4) * 2, 4);
-            while ((g.tpB & 63) != 8) g.tpB += 4;
+            // T rows are ldmatrix operands of the tensor-core upsample (16-byte aligned, odd number of chunks)
+            g.tpB = rc_round_up((g.W + 4) * 2, 16);
+            if (((g.tpB / 16) & 1) == 0) g.tpB += 16;
         }
     }
     pl.zero_bytes = off;
@@ -132,7 +134,7 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
         for (int l = 1; l <= L; ++l) {
             MLevel& g = pl.lv[l];
             g.offT = l < L ? pl.lv[l + 1].off : off;
-            const int e = g.offT + rc_round_up(g.H * g.tpB, 128);
+            const int e = g.offT + rc_round_up(g.H * g.tpB + 32, 128);   // + slack: the last window of a T row may over-read one chunk
             if (e > top) top = e;
         }
         pl.upper_bytes = top;
@@ -197,6 +199,8 @@ RC_HD constexpr int m_make_plan(MPlan& pl, int B, int C, int H, int W, int K, in
     for (int l = 1; l <= L; ++l) {
         pl.lv[l].up_shift = m_lane_shift((pl.lv[l - 1].W + 1) / 2, pl.team_lanes);
         pl.lv[l].up_rpg = rc_div_up(pl.lv[l].H, pl.team_lanes >> pl.lv[l].up_shift);
+        pl.lv[l].up2_shift = m_lane_shift((pl.lv[l].W + 1) / 2, pl.team_lanes);
+        pl.lv[l].up2_rpg = rc_div_up(pl.lv[l].H, pl.team_lanes >> pl.lv[l].up2_shift);
     }
 
     // persistent grid: one CTA per SM; with less work than team slots, spread it over as many SMs as possible
