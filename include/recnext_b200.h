@@ -108,6 +108,19 @@ RECNEXT_API int recattn_down_forward(const recconv_desc* d, const void* w, const
 RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const void* b, const void* x, const void* z, int32_t zH,
                                    int32_t zW, void* y, void* stream);
 
+/*
+ * Fused channel mixer of a RecNeXt block on NCHW tensors: replaces
+ *     x + channel_mixer(norm(y))        with y = token_mixer(x)          model/recnext.py:157-158
+ * where channel_mixer = mlp = 1x1 conv -> GELU -> 1x1 conv (model/recnext.py:125-131) with its ConvNorms folded
+ * (ConvNorm.fuse :75-97) and the eval-mode BatchNorm `norm` (:153) folded into (w1, b1) by the caller:
+ *     out[b,c,p] = x[b,c,p] + b2[c] + sum_h w2[c,h] * gelu(b1[h] + sum_k w1[h,k] * y[b,k,p]),   p = pixel of H*W
+ * y, x, out: [B, C, HW] (= NCHW) in dtype (RECNEXT_BF16 | RECNEXT_F16), 16-byte aligned; w1 [hidden, C], w2 [C, hidden] in
+ * the same dtype; b1 [hidden], b2 [C] fp32.  Inference entry point.  Returns RECNEXT_EUNSUPPORTED (nothing launched)
+ * unless C % 16 == 0, hidden % 16 == 0, HW % 4 == 0 and the tiles fit in shared memory (C <= 256 for hidden = 2C).
+ */
+RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_t HW, int32_t dtype, const void* y, const void* x,
+                                    const void* w1, const float* b1, const void* w2, const float* b2, void* out, void* stream);
+
 /* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);
 

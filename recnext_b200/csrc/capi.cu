@@ -15,6 +15,10 @@
 namespace recnext {
 cudaError_t m_launch(const MPlan&, const KernelArgs&, cudaStream_t);  // recconv_m5.cu: tensor-core forward
 bool m_static_geometry(const MPlan&);
+struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ; };  // ffn_mma.cu
+int ffn_make_plan(FfnPlan&, int B, int C, int HID, int HW, int dtype);
+cudaError_t ffn_launch(const FfnPlan&, const void* y, const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
+                       cudaStream_t stream);
 template <int K, typename T, bool BWD> cudaError_t w_launch(const WPlan&, const KernelArgs&, cudaStream_t);
 typedef cudaError_t (*w_launch_fn)(const WPlan&, const KernelArgs&, cudaStream_t);
 #define W_DECLARE_K(K)                                                                                           \
@@ -292,6 +296,22 @@ RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const v
                        void* y, void* stream) {
     if (zH < 1 || zW < 1) return fail(RECNEXT_EINVAL, "recattn_up_forward: bad z size %dx%d", zH, zW);
     return recattn_launch(d, 2, w, b, x, z, zH, zW, y, stream, "recattn_up_forward");
+}
+
+RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_t HW, int32_t dtype, const void* y, const void* x,
+                        const void* w1, const float* b1, const void* w2, const float* b2, void* out, void* stream) {
+    if (B < 0 || C < 1 || hidden < 1 || HW < 1) return fail(RECNEXT_EINVAL, "recnext_ffn_forward: bad shape [%d,%d,%d] hidden %d", B, C, HW, hidden);
+    if (B == 0) return RECNEXT_OK;
+    if (!y || !x || !w1 || !b1 || !w2 || !b2 || !out) return fail(RECNEXT_EINVAL, "recnext_ffn_forward: null tensor");
+    if ((((uintptr_t)y | (uintptr_t)x | (uintptr_t)out) & 15) != 0 || (((uintptr_t)w1 | (uintptr_t)w2) & 3) != 0)
+        return fail(RECNEXT_EINVAL, "recnext_ffn_forward: activations must be 16-byte aligned");
+    FfnPlan pl;
+    if (ffn_make_plan(pl, B, C, hidden, HW, dtype))
+        return fail(RECNEXT_EUNSUPPORTED, "recnext_ffn_forward: needs 16-bit activations, C %% 16 == 0, hidden %% 16 == 0, HW %% 4 == 0 and "
+                    "(2C + hidden) pixel-tile rows in 227 KB of shared memory (got C=%d hidden=%d HW=%d dtype=%d)", C, hidden, HW, dtype);
+    const cudaError_t e = ffn_launch(pl, y, x, w1, b1, w2, b2, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recnext_ffn_forward: %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
 }
 
 RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d) {

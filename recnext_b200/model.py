@@ -16,8 +16,38 @@ from typing import Callable, Sequence
 import torch
 import torch.nn as nn
 
-from .recattn import RecAttn2d
-from .recconv import RecConv2d
+import ctypes
+import os
+
+from . import _native as N
+from .recattn import RecAttn2d, _timing_start, _timing_stop
+from .recconv import _DTYPES, RecConv2d, _stream
+
+# RECNEXT_FFN=0 keeps the channel mixer on the library path (cuDNN 1x1 convs) for A/B measurements
+FUSED_FFN = os.environ.get("RECNEXT_FFN", "1") != "0"
+
+
+def ffn_forward(y: torch.Tensor, x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """out = x + b2 + W2 gelu(W1 y + b1) per pixel on NCHW tensors — the channel mixer + residual of a RecNeXt block
+    (reference model/recnext.py:125-131,157-158 with every BatchNorm folded) as ONE sm_100a kernel
+    (``recnext_ffn_forward``, include/recnext_b200.h).  16-bit CUDA tensors; no fallback: unsupported shapes raise."""
+    if not (y.is_cuda and x.is_cuda):
+        raise RuntimeError("recnext_b200.ffn_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if y.dtype not in (torch.bfloat16, torch.float16) or x.dtype != y.dtype or w1.dtype != y.dtype or w2.dtype != y.dtype:
+        raise TypeError("ffn_forward: y, x, w1, w2 must share a 16-bit dtype (bfloat16 / float16)")
+    y, x = y.contiguous(), x.contiguous()
+    B, C, H, W = y.shape
+    hid = w1.shape[0]
+    if tuple(w1.shape) != (hid, C) or tuple(w2.shape) != (C, hid) or tuple(x.shape) != tuple(y.shape):
+        raise ValueError(f"ffn_forward: shapes y {tuple(y.shape)} x {tuple(x.shape)} w1 {tuple(w1.shape)} w2 {tuple(w2.shape)}")
+    out = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        ev = _timing_start()
+        N.check(N.lib().recnext_ffn_forward(B, C, hid, H * W, _DTYPES[y.dtype], y.data_ptr(), x.data_ptr(), w1.contiguous().data_ptr(),
+                                            b1.float().contiguous().data_ptr(), w2.contiguous().data_ptr(), b2.float().contiguous().data_ptr(),
+                                            out.data_ptr(), _stream(y)), "recnext_ffn_forward")
+        _timing_stop(ev, 3 * y.numel() * y.element_size(), ("ffn",) + tuple(y.shape))
+    return out
 
 VARIANTS = {  # reference model/recnext.py:369-406
     "recnext_m0": dict(embed_dim=(40, 80, 160, 320), depth=(2, 2, 9, 1)),
@@ -141,7 +171,48 @@ class MetaNeXtBlock(nn.Module):
         self.channel_mixer = mlp(dim, dim * mlp_ratio, act_layer)
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
+    def train(self, mode: bool = True):
+        self._ffn_cache = None  # folded weights belong to the eval-mode statistics
+        return super().train(mode)
+
+    def _ffn_params(self, dtype, device):
+        """(w1, b1, w2, b2) of the fused channel mixer: eval-mode BatchNorm `norm` folded into the first 1x1 conv.
+        y -> s*y + t  =>  W1 (s*y + t) + b1 = (W1 diag(s)) y + (b1 + W1 t)."""
+        c = getattr(self, "_ffn_cache", None)
+        if c is not None and c[0] == (dtype, device):
+            return c[1]
+        fc1, fc2, bn = self.channel_mixer[0], self.channel_mixer[2], self.norm
+        with torch.no_grad():
+            s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+            t = (bn.bias - s * bn.running_mean).float()
+            w1 = fc1.weight.float().view(fc1.out_channels, fc1.in_channels)
+            w2 = fc2.weight.float().view(fc2.out_channels, fc2.in_channels)
+            params = ((w1 * s.view(1, -1)).to(dtype).contiguous(), (fc1.bias.float() + w1 @ t).contiguous(),
+                      w2.to(dtype).contiguous(), fc2.bias.float().contiguous())
+        self._ffn_cache = ((dtype, device), params)
+        return params
+
+    def _ffn_eligible(self, x) -> bool:
+        if self.training or not x.is_cuda or not FUSED_FFN or torch.jit.is_tracing():
+            return False
+        fc1, fc2 = self.channel_mixer[0], self.channel_mixer[2]
+        if not (type(fc1) is nn.Conv2d and type(fc2) is nn.Conv2d and fc1.bias is not None and fc2.bias is not None):
+            return False  # ConvNorms not folded yet (replace_batchnorm / fuse())
+        if not isinstance(self.channel_mixer[1], nn.GELU) or getattr(self.channel_mixer[1], "approximate", "none") != "none":
+            return False
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        C, hid, HW = fc1.in_channels, fc1.out_channels, x.shape[2] * x.shape[3]
+        # measured on B200 (tools/ffn_check.py, batch 256): 0.32 vs 0.77 ms (library path) at [64, 56x56], 0.26 vs 0.41 ms at
+        # [128, 28x28], but 0.38 vs 0.34 ms at [256, 14x14] (one 147 KB CTA per SM: latency bound) — so the wide, small-image
+        # stages keep the library path until the kernel streams its weights through shared memory
+        return (dt in (torch.bfloat16, torch.float16) and C % 16 == 0 and hid % 16 == 0 and HW % 4 == 0 and (HW >= 400 or os.environ.get("RECNEXT_FFN") == "all")
+                and (2 * C + hid) * 144 + 64 <= 227 * 1024)
+
     def forward(self, x):
+        if self._ffn_eligible(x):
+            # token mixer (sm_100a RecConv kernel) -> ONE fused kernel for norm + 1x1 conv + GELU + 1x1 conv + residual
+            y = self.token_mixer(x)
+            return ffn_forward(y, x.to(y.dtype), *self._ffn_params(y.dtype, y.device))
         return x + self.drop_path(self.channel_mixer(self.norm(self.token_mixer(x))))
 
 

@@ -1,0 +1,97 @@
+"""Fused channel mixer (recnext_ffn_forward; reference model/recnext.py:125-131,153,157-158): the kernel against the
+PyTorch graph it replaces, the host-side BatchNorm fold, and the block-level switch in recnext_b200.model."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import TOL_BF16, rel_err
+
+
+def _block(C, stage=0):
+    from oracle.torch_ref import RefRecConv2d
+    from recnext_b200.model import MetaNeXtBlock, replace_batchnorm
+
+    torch.manual_seed(C)
+    blk = MetaNeXtBlock(C, 2, stage=stage, token_mixer=RefRecConv2d)
+    g = torch.Generator().manual_seed(1)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(0.3 * torch.randn(m.num_features, generator=g)); m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(0.7 + 0.6 * torch.rand(m.num_features, generator=g)); m.bias.data.copy_(0.2 * torch.randn(m.num_features, generator=g))
+    blk.eval()
+    return blk, replace_batchnorm
+
+
+def test_bn_fold_into_first_conv_cpu():
+    """host logic: W1 (s*y + t) + b1 == (W1 diag(s)) y + (b1 + W1 t), so the folded parameters reproduce norm -> fc1"""
+    blk, replace_batchnorm = _block(32)
+    y = torch.randn(2, 32, 8, 8)
+    with torch.no_grad():
+        ref = blk.channel_mixer[0](blk.norm(y))            # ConvNorm(BN(y))
+        replace_batchnorm(blk)
+        w1, b1, w2, b2 = blk._ffn_params(torch.float32, torch.device("cpu"))
+        got = F.conv2d(y, w1.view(64, 32, 1, 1), b1)
+        assert rel_err(got.numpy(), ref.numpy()) < 1e-5
+        assert tuple(w2.shape) == (32, 64) and tuple(b2.shape) == (32,)
+    assert not blk._ffn_eligible(y)                        # CPU tensors never take the kernel (and nothing falls back silently)
+    blk.train()
+    assert blk._ffn_cache is None                          # cached fold is dropped when the statistics may change
+
+
+def test_ffn_forward_has_no_cpu_path():
+    from recnext_b200.model import ffn_forward
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ffn_forward(torch.randn(1, 16, 4, 4), torch.randn(1, 16, 4, 4), torch.randn(32, 16), torch.randn(32), torch.randn(16, 32), torch.randn(16))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 64, 56, 56), (4, 128, 28, 28), (3, 256, 14, 14), (3, 80, 28, 28), (2, 160, 14, 14), (2, 32, 6, 6), (2, 48, 10, 18)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_ffn_kernel_vs_torch(shape, dtype):
+    from recnext_b200.model import ffn_forward
+
+    B, C, H, W = shape
+    hid = 2 * C
+    torch.manual_seed(C + H)
+    y = torch.randn(shape, device="cuda").to(dtype); x = torch.randn(shape, device="cuda").to(dtype)
+    w1 = (torch.randn(hid, C, device="cuda") * C ** -0.5).to(dtype); w2 = (torch.randn(C, hid, device="cuda") * hid ** -0.5).to(dtype)
+    b1 = 0.1 * torch.randn(hid, device="cuda"); b2 = 0.1 * torch.randn(C, device="cuda")
+    out = ffn_forward(y, x, w1, b1, w2, b2)
+    ref = x.float() + F.conv2d(F.gelu(F.conv2d(y.float(), w1.float().view(hid, C, 1, 1), b1)), w2.float().view(C, hid, 1, 1), b2)
+    assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < (TOL_BF16 if dtype == torch.bfloat16 else 4e-3)
+
+
+@pytest.mark.gpu
+def test_ffn_unsupported_shapes_are_errors():
+    from recnext_b200.model import ffn_forward
+
+    y = torch.randn(1, 40, 7, 7, device="cuda").bfloat16()   # C % 16 != 0 and HW % 4 != 0
+    with pytest.raises(RuntimeError, match="recnext_ffn_forward"):
+        ffn_forward(y, y, torch.randn(80, 40, device="cuda").bfloat16(), torch.randn(80, device="cuda"), torch.randn(40, 80, device="cuda").bfloat16(),
+                    torch.randn(40, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_block_with_fused_ffn_matches_library_path(monkeypatch):
+    """MetaNeXtBlock in eval mode with folded ConvNorms: fused kernel path vs the PyTorch module graph (same parameters)"""
+    import recnext_b200.model as M
+
+    blk, replace_batchnorm = _block(64)
+    replace_batchnorm(blk)
+    blk.cuda()
+    x = torch.randn(4, 64, 56, 56, device="cuda")
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert blk._ffn_eligible(x)
+        y_fused = blk(x)
+        monkeypatch.setattr(M, "FUSED_FFN", False)
+        assert not blk._ffn_eligible(x)
+        y_lib = blk(x)
+    ref32 = None
+    with torch.no_grad():
+        ref32 = x + blk.channel_mixer(blk.norm(blk.token_mixer(x)))
+    assert y_fused.dtype == torch.bfloat16
+    assert rel_err(y_fused.float().cpu().numpy(), ref32.cpu().numpy()) < TOL_BF16
+    assert rel_err(y_lib.float().cpu().numpy(), ref32.cpu().numpy()) < TOL_BF16
