@@ -15,7 +15,7 @@
 namespace recnext {
 cudaError_t m_launch(const MPlan&, const KernelArgs&, cudaStream_t);  // recconv_m5.cu: tensor-core forward
 bool m_static_geometry(const MPlan&);
-struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ; };  // ffn_mma.cu
+struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ, staged, offW, kc; };  // ffn_mma.cu
 int ffn_make_plan(FfnPlan&, int B, int C, int HID, int HW, int dtype);
 cudaError_t ffn_launch(const FfnPlan&, const void* y, const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
                        cudaStream_t stream);

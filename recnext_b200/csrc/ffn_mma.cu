@@ -36,6 +36,8 @@ struct FfnPlan {
     int smem_bytes;
     int dtype;        // 1 bf16, 2 f16
     int NQ;           // n-tiles swept per unit: 8 or 4
+    int staged, offW; // wide stages: weights stream through shared memory (kFfnStages chunk buffers at offW)
+    int kc;           // staged: K-chunk (64 or 32)
 };
 
 template <typename T> struct FfnT;
@@ -210,6 +212,158 @@ __global__ void __launch_bounds__(256) recnext_ffn_kernel(const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Wide stages (C >= 192): the weights no longer sit in L1, and eight warps per SM cannot hide the L2 latency of
+// per-fragment loads (ncu: long-scoreboard stalls).  Here the weights of one ROUND (8 m-tiles = 128 rows, one per warp)
+// stream through shared memory in K-chunks with a 3-stage cp.async pipeline (full 128-byte row segments, issued
+// two chunks ahead) and the A fragments come from ldmatrix.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f_ldsm4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+
+constexpr int kFfnStages = 3;
+
+// rows [r0, r0 + 128) of  D = W[rows x K] * S[K x pixels]; warp w computes rows r0 + 16 w .. + 15 (if < rows_total).
+// Wb: shared address of kFfnStages chunk buffers of 128 rows x (KC * 2 + 16) bytes.  Ends with every warp past its last
+// read of Wb NOT guaranteed: the caller synchronises before the buffers are reused.
+template <typename T, int NQ, int KC>
+__device__ __forceinline__ void ffn_round_staged(float (&acc)[NQ][4], const T* __restrict__ W, int K, int rows_total, int r0, uint32_t S, int PB,
+                                                 uint32_t Wb, int tid) {
+    constexpr int WP = KC * 2 + 16;                 // chunk row pitch (bytes): odd number of 16-byte pieces
+    constexpr int PPR = KC * 2 / 16;                // 16-byte pieces per chunk row
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nch = K / KC;
+    auto issue = [&](int c) {
+        const uint32_t dst = Wb + (uint32_t)(c % kFfnStages) * (uint32_t)(128 * WP);
+        for (int i = tid; i < 128 * PPR; i += 256) {
+            const int row = i / PPR, pc = i - row * PPR;
+            if (r0 + row < rows_total)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (uint32_t)(row * WP + pc * 16)),
+                             "l"(W + (long)(r0 + row) * K + c * KC + pc * 8) : "memory");
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < kFfnStages - 1; ++s) {
+        if (s < nch) issue(s);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    const bool active = r0 + warp * 16 < rows_total;
+    const uint32_t arow = (uint32_t)((warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * WP) + (uint32_t)(lane >> 4) * 16u;
+    const uint32_t sb = S + (uint32_t)(lane & 15) * (uint32_t)PB + (uint32_t)(lane >> 4) * 16u;
+    for (int c = 0; c < nch; ++c) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kFfnStages - 2) : "memory");
+        __syncthreads();
+        if (c + kFfnStages - 1 < nch) issue(c + kFfnStages - 1);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        if (active) {
+            const uint32_t wbuf = Wb + (uint32_t)(c % kFfnStages) * (uint32_t)(128 * WP) + arow;
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks) {
+                uint32_t a0, a1, a2, a3;
+                f_ldsm4(a0, a1, a2, a3, wbuf + (uint32_t)ks * 32u);
+                const uint32_t srow = sb + (uint32_t)((c * KC + ks * 16) * PB);
+#pragma unroll
+                for (int q = 0; q < NQ; q += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    f_ldsm4t(b0, b1, b2, b3, srow + (uint32_t)q * 16u);
+                    FfnT<T>::mma(acc[q], a0, a1, a2, a3, b0, b1);
+                    if (q + 1 < NQ) FfnT<T>::mma(acc[q + 1], a0, a1, a2, a3, b2, b3);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int KC1, int KC2>
+__global__ void __launch_bounds__(256) recnext_ffn_staged_kernel(const __grid_constant__ FfnPlan pl, const T* __restrict__ y, const T* __restrict__ x,
+                                                                 const T* __restrict__ w1, const float* __restrict__ b1, const T* __restrict__ w2,
+                                                                 const float* __restrict__ b2, T* __restrict__ out) {
+    constexpr int NQ = 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int img = blockIdx.x / pl.tiles, tile = blockIdx.x - img * pl.tiles;
+    const int C = pl.C, HID = pl.HID, HW = pl.HW, PB = pl.PB;
+    const int p0 = tile * pl.NTN * 8;
+    const int np = (HW - p0) < pl.NTN * 8 ? (HW - p0) : pl.NTN * 8;
+    const uint32_t Ys = (uint32_t)__cvta_generic_to_shared(smem), Xs = Ys + (uint32_t)pl.offX, Hs = Ys + (uint32_t)pl.offH, Wb = Ys + (uint32_t)pl.offW;
+    const long ibase = (long)img * C * HW + p0;
+    {
+        const int cpr = pl.NTN * 16 / pl.chunkB, epc = pl.chunkB / 2;
+        for (int i = tid; i < C * cpr; i += 256) {
+            const int row = i / cpr, ch = i - row * cpr;
+            const uint32_t so = (uint32_t)row * (uint32_t)PB + (uint32_t)ch * (uint32_t)pl.chunkB;
+            if (ch * epc < np) {
+                f_cp_async(Ys + so, y + ibase + (long)row * HW + ch * epc, pl.chunkB);
+                f_cp_async(Xs + so, x + ibase + (long)row * HW + ch * epc, pl.chunkB);
+            } else {
+                if (pl.chunkB == 16) { *reinterpret_cast<uint4*>(smem + so) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(smem + pl.offX + so) = make_uint4(0, 0, 0, 0); }
+                else { *reinterpret_cast<uint2*>(smem + so) = make_uint2(0, 0); *reinterpret_cast<uint2*>(smem + pl.offX + so) = make_uint2(0, 0); }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+    }
+    const int nq = pl.NTN;
+    // ---- GEMM 1 + bias + GELU
+    for (int r0 = 0; r0 < HID; r0 += 128) {
+        float acc[NQ][4];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
+        ffn_round_staged<T, NQ, KC1>(acc, w1, C, HID, r0, Ys, PB, Wb, tid);
+        const int m0 = r0 + warp * 16;
+        if (m0 < HID) {
+            const float ba = __ldg(b1 + m0 + g), bb = __ldg(b1 + m0 + g + 8);
+            const uint32_t ha = Hs + (uint32_t)(m0 + g) * (uint32_t)PB + (uint32_t)(4 * t), hb = ha + 8u * (uint32_t)PB;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q < nq) {
+                    const uint32_t va = FfnT<T>::pack(f_gelu(acc[q][0] + ba), f_gelu(acc[q][1] + ba));
+                    const uint32_t vb = FfnT<T>::pack(f_gelu(acc[q][2] + bb), f_gelu(acc[q][3] + bb));
+                    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(ha + 16u * q), "r"(va) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(hb + 16u * q), "r"(vb) : "memory");
+                }
+        }
+        __syncthreads();   // weight buffers are reused by the next round; Hs complete before GEMM 2
+    }
+    // ---- GEMM 2 + bias + residual
+    for (int r0 = 0; r0 < C; r0 += 128) {
+        float acc[NQ][4];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
+        ffn_round_staged<T, NQ, KC2>(acc, w2, HID, C, r0, Hs, PB, Wb, tid);
+        const int m0 = r0 + warp * 16;
+        if (m0 < C) {
+            const float ba = __ldg(b2 + m0 + g), bb = __ldg(b2 + m0 + g + 8);
+            const uint32_t xa = Xs + (uint32_t)(m0 + g) * (uint32_t)PB + (uint32_t)(4 * t), xb = xa + 8u * (uint32_t)PB;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q < nq) {
+                    uint32_t ra, rb;
+                    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(ra) : "r"(xa + 16u * q));
+                    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(rb) : "r"(xb + 16u * q));
+                    const float2 fa = FfnT<T>::unpack(ra), fb = FfnT<T>::unpack(rb);
+                    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(xa + 16u * q), "r"(FfnT<T>::pack(fa.x + (acc[q][0] + ba), fa.y + (acc[q][1] + ba))) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(xb + 16u * q), "r"(FfnT<T>::pack(fb.x + (acc[q][2] + bb), fb.y + (acc[q][3] + bb))) : "memory");
+                }
+        }
+        __syncthreads();
+    }
+    {
+        const int cpr = pl.NTN * 16 / pl.chunkB, epc = pl.chunkB / 2;
+        for (int i = tid; i < C * cpr; i += 256) {
+            const int row = i / cpr, ch = i - row * cpr;
+            if (ch * epc >= np) continue;
+            const unsigned char* s = smem + pl.offX + (long)row * PB + ch * pl.chunkB;
+            T* d = out + ibase + (long)row * HW + ch * epc;
+            if (pl.chunkB == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+            else *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(s);
+        }
+    }
+}
+
 // 0 ok; 1 unsupported shape (caller keeps the library path); fills pl
 int ffn_make_plan(FfnPlan& pl, int B, int C, int HID, int HW, int dtype) {
     if (B < 1 || C < 16 || HID < 16 || HW < 1) return 1;
@@ -233,6 +387,17 @@ int ffn_make_plan(FfnPlan& pl, int B, int C, int HID, int HW, int dtype) {
     pl.offH = 2 * C * pl.PB;
     pl.smem_bytes = (2 * C + HID) * pl.PB + 64;       // + slack: a paired ldmatrix may over-read one chunk past the last row
     if (pl.smem_bytes > 227 * 1024) return 1;
+    // staged weights: C >= 192 (weights beyond L1), 8-wide tiles, K multiples of 32; RECNEXT_FFN_STAGE=0|1 overrides
+    pl.staged = (C >= 192 && nq == 8 && (C % 32) == 0 && (HID % 32) == 0) ? 1 : 0;
+    { const char* e = getenv("RECNEXT_FFN_STAGE"); if (e) pl.staged = (atoi(e) != 0 && nq == 8 && (C % 32) == 0 && (HID % 32) == 0) ? 1 : 0; }
+    if (pl.staged) {
+        pl.offW = (2 * C + HID) * pl.PB + 64;
+        int kc = ((C % 64) == 0 && (HID % 64) == 0) ? 64 : 32;
+        if (pl.offW + 3 * 128 * (kc * 2 + 16) > 227 * 1024) kc = 32;
+        const int bytes = pl.offW + 3 * 128 * (kc * 2 + 16);
+        pl.kc = kc;
+        if (bytes > 227 * 1024) pl.staged = 0; else pl.smem_bytes = bytes;
+    }
     return 0;
 }
 
@@ -248,6 +413,23 @@ cudaError_t ffn_launch(const FfnPlan& pl, const void* y, const void* x, const vo
         configured = 1;
     }
     const int grid = pl.B * pl.tiles;
+    if (pl.staged) {
+        static int configured_s = 0;
+        if (!configured_s) {
+            cudaError_t e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__nv_bfloat16, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__nv_bfloat16, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__half, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__half, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return e;
+            configured_s = 1;
+        }
+        const bool k64 = pl.kc == 64;
+#define FFN_LAUNCH_S(TT, KC) recnext_ffn_staged_kernel<TT, KC, KC><<<grid, 256, pl.smem_bytes, stream>>>(pl, (const TT*)y, (const TT*)x, (const TT*)w1, b1, (const TT*)w2, b2, (TT*)out)
+        if (pl.dtype == 1) { if (k64) FFN_LAUNCH_S(__nv_bfloat16, 64); else FFN_LAUNCH_S(__nv_bfloat16, 32); }
+        else { if (k64) FFN_LAUNCH_S(__half, 64); else FFN_LAUNCH_S(__half, 32); }
+#undef FFN_LAUNCH_S
+        return cudaGetLastError();
+    }
 #define FFN_LAUNCH(TT, NQV) recnext_ffn_kernel<TT, NQV><<<grid, 256, pl.smem_bytes, stream>>>(pl, (const TT*)y, (const TT*)x, (const TT*)w1, b1, (const TT*)w2, b2, (TT*)out)
     if (pl.dtype == 1) { if (pl.NQ == 8) FFN_LAUNCH(__nv_bfloat16, 8); else FFN_LAUNCH(__nv_bfloat16, 4); }
     else { if (pl.NQ == 8) FFN_LAUNCH(__half, 8); else FFN_LAUNCH(__half, 4); }

@@ -202,10 +202,12 @@ class MetaNeXtBlock(nn.Module):
             return False
         dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         C, hid, HW = fc1.in_channels, fc1.out_channels, x.shape[2] * x.shape[3]
-        # measured on B200 (tools/ffn_check.py, batch 256): 0.32 vs 0.77 ms (library path) at [64, 56x56], 0.26 vs 0.41 ms at
-        # [128, 28x28], but 0.38 vs 0.34 ms at [256, 14x14] (one 147 KB CTA per SM: latency bound) — so the wide, small-image
-        # stages keep the library path until the kernel streams its weights through shared memory
-        return (dt in (torch.bfloat16, torch.float16) and C % 16 == 0 and hid % 16 == 0 and HW % 4 == 0 and (HW >= 400 or os.environ.get("RECNEXT_FFN") == "all")
+        # measured on B200 (tools/ffn_check.py, batch 256; kernel vs the library path it replaces): [64, 56x56] 0.28 vs 0.78 ms,
+        # [128, 28x28] 0.24 vs 0.41 ms, [256, 14x14] 0.24 vs 0.34 ms (weights staged through shared memory: C >= 192 and
+        # C % 32 == 0).  Narrow stages with small images (e.g. [160, 14x14]) stay on the library path: 0.46 vs 0.51 ms is a wash
+        staged = 192 <= C <= 256 and C % 32 == 0 and hid % 32 == 0   # ([320, 14x14]: 0.45 vs 0.43 ms, not worth it yet)
+        return (dt in (torch.bfloat16, torch.float16) and C % 16 == 0 and hid % 16 == 0 and HW % 4 == 0
+                and (HW >= 400 or staged or os.environ.get("RECNEXT_FFN") == "all")
                 and (2 * C + hid) * 144 + 64 <= 227 * 1024)
 
     def forward(self, x):
