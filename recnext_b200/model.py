@@ -161,6 +161,29 @@ class RecNextStem(nn.Module):
         return self.stem(x)
 
 
+def _ffn_shape_ok(block: nn.Module, x: torch.Tensor) -> bool:
+    """Does this block (eval mode, ConvNorms folded) take the fused channel-mixer kernel for input x?"""
+    if block.training or not x.is_cuda or not FUSED_FFN or torch.jit.is_tracing():
+        return False
+    fc1, fc2 = block.channel_mixer[0], block.channel_mixer[2]
+    if not (type(fc1) is nn.Conv2d and type(fc2) is nn.Conv2d and fc1.bias is not None and fc2.bias is not None):
+        return False  # ConvNorms not folded yet (replace_batchnorm / fuse())
+    if not isinstance(block.channel_mixer[1], nn.GELU) or getattr(block.channel_mixer[1], "approximate", "none") != "none":
+        return False
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+    if x.dtype != dt and not isinstance(block, MetaNeXtBlock):
+        return False
+    C, hid, HW = fc1.in_channels, fc1.out_channels, x.shape[2] * x.shape[3]
+    # measured on B200 (tools/ffn_check.py, batch 256; kernel vs the library path it replaces): [64, 56x56] 0.28 vs 0.78 ms,
+    # [128, 28x28] 0.24 vs 0.41 ms, [256, 14x14] 0.24 vs 0.34 ms (weights staged through shared memory: 192 <= C <= 256 and
+    # C % 32 == 0; [320, 14x14] 0.45 vs 0.43 ms is not worth it yet).  Narrow stages with small images stay on the library
+    # path ([160, 14x14]: 0.46 vs 0.51 ms is a wash)
+    staged = 192 <= C <= 256 and C % 32 == 0 and hid % 32 == 0
+    return (dt in (torch.bfloat16, torch.float16) and C % 16 == 0 and hid % 16 == 0 and HW % 4 == 0
+            and (HW >= 400 or staged or os.environ.get("RECNEXT_FFN") == "all")
+            and (2 * C + hid) * 144 + 64 <= 227 * 1024)
+
+
 class MetaNeXtBlock(nn.Module):
     """x + drop_path(channel_mixer(norm(token_mixer(x)))), token_mixer = RecConv2d(level = 4 - stage, k = 5)."""
 
@@ -193,22 +216,7 @@ class MetaNeXtBlock(nn.Module):
         return params
 
     def _ffn_eligible(self, x) -> bool:
-        if self.training or not x.is_cuda or not FUSED_FFN or torch.jit.is_tracing():
-            return False
-        fc1, fc2 = self.channel_mixer[0], self.channel_mixer[2]
-        if not (type(fc1) is nn.Conv2d and type(fc2) is nn.Conv2d and fc1.bias is not None and fc2.bias is not None):
-            return False  # ConvNorms not folded yet (replace_batchnorm / fuse())
-        if not isinstance(self.channel_mixer[1], nn.GELU) or getattr(self.channel_mixer[1], "approximate", "none") != "none":
-            return False
-        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
-        C, hid, HW = fc1.in_channels, fc1.out_channels, x.shape[2] * x.shape[3]
-        # measured on B200 (tools/ffn_check.py, batch 256; kernel vs the library path it replaces): [64, 56x56] 0.28 vs 0.78 ms,
-        # [128, 28x28] 0.24 vs 0.41 ms, [256, 14x14] 0.24 vs 0.34 ms (weights staged through shared memory: C >= 192 and
-        # C % 32 == 0).  Narrow stages with small images (e.g. [160, 14x14]) stay on the library path: 0.46 vs 0.51 ms is a wash
-        staged = 192 <= C <= 256 and C % 32 == 0 and hid % 32 == 0   # ([320, 14x14]: 0.45 vs 0.43 ms, not worth it yet)
-        return (dt in (torch.bfloat16, torch.float16) and C % 16 == 0 and hid % 16 == 0 and HW % 4 == 0
-                and (HW >= 400 or staged or os.environ.get("RECNEXT_FFN") == "all")
-                and (2 * C + hid) * 144 + 64 <= 227 * 1024)
+        return _ffn_shape_ok(self, x)
 
     def forward(self, x):
         if self._ffn_eligible(x):
@@ -239,8 +247,22 @@ class Downsample(nn.Module):
         self.norm = nn.BatchNorm2d(dim * 2)
         self.channel_mixer = mlp(dim * 2, dim * 2 * mlp_ratio, act_layer)
 
+    def train(self, mode: bool = True):
+        self._ffn_cache = None
+        return super().train(mode)
+
     def forward(self, x):
         x = self.norm(self.token_mixer(x))
+        if _ffn_shape_ok(self, x):
+            # x + mlp(x) (model/recnext.py:145-146) as the same fused kernel: the mixer input is also the residual
+            c = getattr(self, "_ffn_cache", None)
+            if c is None or c[0] != (x.dtype, x.device):
+                fc1, fc2 = self.channel_mixer[0], self.channel_mixer[2]
+                with torch.no_grad():
+                    c = ((x.dtype, x.device), (fc1.weight.view(fc1.out_channels, -1).to(x.dtype).contiguous(), fc1.bias.float().contiguous(),
+                                               fc2.weight.view(fc2.out_channels, -1).to(x.dtype).contiguous(), fc2.bias.float().contiguous()))
+                self._ffn_cache = c
+            return ffn_forward(x, x, *c[1])
         return x + self.channel_mixer(x)
 
 
