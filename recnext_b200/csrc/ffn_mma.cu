@@ -227,16 +227,16 @@ constexpr int kFfnStages = 3;
 // rows [r0, r0 + 128) of  D = W[rows x K] * S[K x pixels]; warp w computes rows r0 + 16 w .. + 15 (if < rows_total).
 // Wb: shared address of kFfnStages chunk buffers of 128 rows x (KC * 2 + 16) bytes.  Ends with every warp past its last
 // read of Wb NOT guaranteed: the caller synchronises before the buffers are reused.
-template <typename T, int NQ, int KC>
+template <typename T, int NQ, int KC, int NTHREADS>
 __device__ __forceinline__ void ffn_round_staged(float (&acc)[NQ][4], const T* __restrict__ W, int K, int rows_total, int r0, uint32_t S, int PB,
                                                  uint32_t Wb, int tid) {
     constexpr int WP = KC * 2 + 16;                 // chunk row pitch (bytes): odd number of 16-byte pieces
     constexpr int PPR = KC * 2 / 16;                // 16-byte pieces per chunk row
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = (tid >> 5) & 7, nhalf = tid >> 8;   // 16 warps: m-tile = warp % 8, n-tiles [NQ * nhalf, +NQ)
     const int nch = K / KC;
     auto issue = [&](int c) {
         const uint32_t dst = Wb + (uint32_t)(c % kFfnStages) * (uint32_t)(128 * WP);
-        for (int i = tid; i < 128 * PPR; i += 256) {
+        for (int i = tid; i < 128 * PPR; i += NTHREADS) {
             const int row = i / PPR, pc = i - row * PPR;
             if (r0 + row < rows_total)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (uint32_t)(row * WP + pc * 16)),
@@ -250,7 +250,7 @@ __device__ __forceinline__ void ffn_round_staged(float (&acc)[NQ][4], const T* _
     }
     const bool active = r0 + warp * 16 < rows_total;
     const uint32_t arow = (uint32_t)((warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * WP) + (uint32_t)(lane >> 4) * 16u;
-    const uint32_t sb = S + (uint32_t)(lane & 15) * (uint32_t)PB + (uint32_t)(lane >> 4) * 16u;
+    const uint32_t sb = S + (uint32_t)(lane & 15) * (uint32_t)PB + (uint32_t)(lane >> 4) * 16u + (uint32_t)(nhalf * NQ) * 16u;
     for (int c = 0; c < nch; ++c) {
         asm volatile("cp.async.wait_group %0;\n" ::"n"(kFfnStages - 2) : "memory");
         __syncthreads();
@@ -276,12 +276,12 @@ __device__ __forceinline__ void ffn_round_staged(float (&acc)[NQ][4], const T* _
 }
 
 template <typename T, int KC1, int KC2>
-__global__ void __launch_bounds__(256) recnext_ffn_staged_kernel(const __grid_constant__ FfnPlan pl, const T* __restrict__ y, const T* __restrict__ x,
+__global__ void __launch_bounds__(512) recnext_ffn_staged_kernel(const __grid_constant__ FfnPlan pl, const T* __restrict__ y, const T* __restrict__ x,
                                                                  const T* __restrict__ w1, const float* __restrict__ b1, const T* __restrict__ w2,
                                                                  const float* __restrict__ b2, T* __restrict__ out) {
-    constexpr int NQ = 8;
+    constexpr int NQ = 4;          // n-tiles per warp: 16 warps = 8 m-tiles x 2 halves of the 8-wide pixel tile
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & 7, nq0 = (tid >> 8) * NQ;
     const int g = lane >> 2, t = lane & 3;
     const int img = blockIdx.x / pl.tiles, tile = blockIdx.x - img * pl.tiles;
     const int C = pl.C, HID = pl.HID, HW = pl.HW, PB = pl.PB;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) recnext_ffn_staged_kernel(const __grid_co
     const long ibase = (long)img * C * HW + p0;
     {
         const int cpr = pl.NTN * 16 / pl.chunkB, epc = pl.chunkB / 2;
-        for (int i = tid; i < C * cpr; i += 256) {
+        for (int i = tid; i < C * cpr; i += 512) {
             const int row = i / cpr, ch = i - row * cpr;
             const uint32_t so = (uint32_t)row * (uint32_t)PB + (uint32_t)ch * (uint32_t)pl.chunkB;
             if (ch * epc < np) {
@@ -312,14 +312,14 @@ __global__ void __launch_bounds__(256) recnext_ffn_staged_kernel(const __grid_co
         float acc[NQ][4];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
-        ffn_round_staged<T, NQ, KC1>(acc, w1, C, HID, r0, Ys, PB, Wb, tid);
+        ffn_round_staged<T, NQ, KC1, 512>(acc, w1, C, HID, r0, Ys, PB, Wb, tid);
         const int m0 = r0 + warp * 16;
         if (m0 < HID) {
             const float ba = __ldg(b1 + m0 + g), bb = __ldg(b1 + m0 + g + 8);
-            const uint32_t ha = Hs + (uint32_t)(m0 + g) * (uint32_t)PB + (uint32_t)(4 * t), hb = ha + 8u * (uint32_t)PB;
+            const uint32_t ha = Hs + (uint32_t)(m0 + g) * (uint32_t)PB + (uint32_t)(16 * nq0 + 4 * t), hb = ha + 8u * (uint32_t)PB;
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                if (q < nq) {
+                if (nq0 + q < nq) {
                     const uint32_t va = FfnT<T>::pack(f_gelu(acc[q][0] + ba), f_gelu(acc[q][1] + ba));
                     const uint32_t vb = FfnT<T>::pack(f_gelu(acc[q][2] + bb), f_gelu(acc[q][3] + bb));
                     asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(ha + 16u * q), "r"(va) : "memory");
@@ -333,14 +333,14 @@ __global__ void __launch_bounds__(256) recnext_ffn_staged_kernel(const __grid_co
         float acc[NQ][4];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
-        ffn_round_staged<T, NQ, KC2>(acc, w2, HID, C, r0, Hs, PB, Wb, tid);
+        ffn_round_staged<T, NQ, KC2, 512>(acc, w2, HID, C, r0, Hs, PB, Wb, tid);
         const int m0 = r0 + warp * 16;
         if (m0 < C) {
             const float ba = __ldg(b2 + m0 + g), bb = __ldg(b2 + m0 + g + 8);
-            const uint32_t xa = Xs + (uint32_t)(m0 + g) * (uint32_t)PB + (uint32_t)(4 * t), xb = xa + 8u * (uint32_t)PB;
+            const uint32_t xa = Xs + (uint32_t)(m0 + g) * (uint32_t)PB + (uint32_t)(16 * nq0 + 4 * t), xb = xa + 8u * (uint32_t)PB;
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                if (q < nq) {
+                if (nq0 + q < nq) {
                     uint32_t ra, rb;
                     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(ra) : "r"(xa + 16u * q));
                     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(rb) : "r"(xb + 16u * q));
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) recnext_ffn_staged_kernel(const __grid_co
     }
     {
         const int cpr = pl.NTN * 16 / pl.chunkB, epc = pl.chunkB / 2;
-        for (int i = tid; i < C * cpr; i += 256) {
+        for (int i = tid; i < C * cpr; i += 512) {
             const int row = i / cpr, ch = i - row * cpr;
             if (ch * epc >= np) continue;
             const unsigned char* s = smem + pl.offX + (long)row * PB + ch * pl.chunkB;
@@ -424,7 +424,7 @@ cudaError_t ffn_launch(const FfnPlan& pl, const void* y, const void* x, const vo
             configured_s = 1;
         }
         const bool k64 = pl.kc == 64;
-#define FFN_LAUNCH_S(TT, KC) recnext_ffn_staged_kernel<TT, KC, KC><<<grid, 256, pl.smem_bytes, stream>>>(pl, (const TT*)y, (const TT*)x, (const TT*)w1, b1, (const TT*)w2, b2, (TT*)out)
+#define FFN_LAUNCH_S(TT, KC) recnext_ffn_staged_kernel<TT, KC, KC><<<grid, 512, pl.smem_bytes, stream>>>(pl, (const TT*)y, (const TT*)x, (const TT*)w1, b1, (const TT*)w2, b2, (TT*)out)
         if (pl.dtype == 1) { if (k64) FFN_LAUNCH_S(__nv_bfloat16, 64); else FFN_LAUNCH_S(__nv_bfloat16, 32); }
         else { if (k64) FFN_LAUNCH_S(__half, 64); else FFN_LAUNCH_S(__half, 32); }
 #undef FFN_LAUNCH_S
