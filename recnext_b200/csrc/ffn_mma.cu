@@ -234,14 +234,22 @@ __device__ __forceinline__ void ffn_round_staged(float (&acc)[NQ][4], const T* _
     constexpr int PPR = KC * 2 / 16;                // 16-byte pieces per chunk row
     const int lane = tid & 31, warp = (tid >> 5) & 7, nhalf = tid >> 8;   // 16 warps: m-tile = warp % 8, n-tiles [NQ * nhalf, +NQ)
     const int nch = K / KC;
+    // this thread's pieces of a chunk: piece i = tid + j * NTHREADS -> (row, 16-byte piece); loop invariant
+    constexpr int NP = (128 * PPR + NTHREADS - 1) / NTHREADS;
+    const T* gsrc[NP];
+    uint32_t sdst[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const int i = tid + j * NTHREADS, row = i / PPR, pc = i - row * PPR;
+        const bool ok = i < 128 * PPR && r0 + row < rows_total;
+        gsrc[j] = ok ? W + (long)(r0 + row) * K + pc * 8 : nullptr;
+        sdst[j] = Wb + (uint32_t)(row * WP + pc * 16);
+    }
     auto issue = [&](int c) {
-        const uint32_t dst = Wb + (uint32_t)(c % kFfnStages) * (uint32_t)(128 * WP);
-        for (int i = tid; i < 128 * PPR; i += NTHREADS) {
-            const int row = i / PPR, pc = i - row * PPR;
-            if (r0 + row < rows_total)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (uint32_t)(row * WP + pc * 16)),
-                             "l"(W + (long)(r0 + row) * K + c * KC + pc * 8) : "memory");
-        }
+        const uint32_t boff = (uint32_t)(c % kFfnStages) * (uint32_t)(128 * WP);
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+            if (gsrc[j]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst[j] + boff), "l"(gsrc[j] + c * KC) : "memory");
     };
 #pragma unroll
     for (int s = 0; s < kFfnStages - 1; ++s) {
@@ -257,18 +265,27 @@ __device__ __forceinline__ void ffn_round_staged(float (&acc)[NQ][4], const T* _
         if (c + kFfnStages - 1 < nch) issue(c + kFfnStages - 1);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         if (active) {
+            // fragments of k-step ks + 1 are fetched before the MMAs of k-step ks are issued (the asm statements keep program
+            // order, so the overlap of ldmatrix latency with the tensor pipe has to be written out)
             const uint32_t wbuf = Wb + (uint32_t)(c % kFfnStages) * (uint32_t)(128 * WP) + arow;
+            const uint32_t srow0 = sb + (uint32_t)((c * KC) * PB);
+            uint32_t A[2][4], B[2][NQ / 2][4];
+            f_ldsm4(A[0][0], A[0][1], A[0][2], A[0][3], wbuf);
+#pragma unroll
+            for (int q = 0; q < NQ; q += 2) f_ldsm4t(B[0][q / 2][0], B[0][q / 2][1], B[0][q / 2][2], B[0][q / 2][3], srow0 + (uint32_t)q * 16u);
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks) {
-                uint32_t a0, a1, a2, a3;
-                f_ldsm4(a0, a1, a2, a3, wbuf + (uint32_t)ks * 32u);
-                const uint32_t srow = sb + (uint32_t)((c * KC + ks * 16) * PB);
+                const int cur = ks & 1, nxt = cur ^ 1;
+                if (ks + 1 < KC / 16) {
+                    f_ldsm4(A[nxt][0], A[nxt][1], A[nxt][2], A[nxt][3], wbuf + (uint32_t)(ks + 1) * 32u);
+                    const uint32_t srow = srow0 + (uint32_t)(((ks + 1) * 16) * PB);
+#pragma unroll
+                    for (int q = 0; q < NQ; q += 2) f_ldsm4t(B[nxt][q / 2][0], B[nxt][q / 2][1], B[nxt][q / 2][2], B[nxt][q / 2][3], srow + (uint32_t)q * 16u);
+                }
 #pragma unroll
                 for (int q = 0; q < NQ; q += 2) {
-                    uint32_t b0, b1, b2, b3;
-                    f_ldsm4t(b0, b1, b2, b3, srow + (uint32_t)q * 16u);
-                    FfnT<T>::mma(acc[q], a0, a1, a2, a3, b0, b1);
-                    if (q + 1 < NQ) FfnT<T>::mma(acc[q + 1], a0, a1, a2, a3, b2, b3);
+                    FfnT<T>::mma(acc[q], A[cur][0], A[cur][1], A[cur][2], A[cur][3], B[cur][q / 2][0], B[cur][q / 2][1]);
+                    if (q + 1 < NQ) FfnT<T>::mma(acc[q + 1], A[cur][0], A[cur][1], A[cur][2], A[cur][3], B[cur][q / 2][2], B[cur][q / 2][3]);
                 }
             }
         }
