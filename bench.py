@@ -271,7 +271,7 @@ def main():
     per_shape, dom = [], {"bytes": 0, "ms": 0.0, "n": 0}
     for shape, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
         if isinstance(shape[0], str):   # RecAttn2d pieces: ("down" | "up", B, C, H, W)
-            kern = "recnext_ffn_kernel" if shape[0] == "ffn" else "recconv_mfwd_kernel/" + shape[0]
+            kern = {"ffn": "recnext_ffn_kernel", "dwdown": "recnext_dwdown_kernel"}.get(shape[0], "recconv_mfwd_kernel/" + shape[0])
         else:
             level = {56: 4, 28: 3, 14: 2, 7: 1}.get(shape[2], 0) if RES == 224 else None
             desc = RC.plan_describe(shape, 5, level, "bilinear", torch.bfloat16, False, False) if level is not None else ""
@@ -279,7 +279,7 @@ def main():
         gbs = g["bytes"] / (g["ms"] * 1e-3) * 1e-9 if g["ms"] > 0 else 0.0
         per_shape.append({"shape": list(shape), "kernel": kern, "launches_per_step": g["n"] / max(args.steps, 1),
                           "avg_launch_ms": round(g["ms"] / g["n"], 5), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
-        if kern.startswith("recconv_mfwd") or ("_a" in MODEL and kern != "recnext_ffn_kernel"):
+        if kern.startswith("recconv_mfwd") or ("_a" in MODEL and kern.startswith("recconv_mfwd_kernel/")):
             dom["bytes"] += g["bytes"]; dom["ms"] += g["ms"]; dom["n"] += g["n"]
     if dom["n"] == 0:
         dom = {"bytes": sum(r["bytes"] for r in launches), "ms": sum(r["ms"] for r in launches), "n": len(launches)}

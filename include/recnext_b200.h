@@ -121,6 +121,16 @@ RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const v
 RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_t HW, int32_t dtype, const void* y, const void* x,
                                     const void* w1, const float* b1, const void* w2, const float* b2, void* out, void* stream);
 
+/*
+ * Token mixer of a `Downsample` block: depthwise 7x7 stride-2 conv with channel multiplier 2 and the
+ * eval-mode BatchNorm that follows it folded into (w, b) by the caller — replaces
+ *     self.norm(self.token_mixer(x))      model/recnext.py:137-138,145
+ * x: [B, C, H, W], out: [B, 2C, (H-1)/2+1, (W-1)/2+1] in dtype (RECNEXT_BF16 | RECNEXT_F16); w: [2C, 1, 7, 7] fp32, b: [2C] fp32.
+ * Inference entry point.  RECNEXT_EUNSUPPORTED if a padded fp32 plane does not fit in shared memory.
+ */
+RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w,
+                                       const float* b, void* out, void* stream);
+
 /* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);
 

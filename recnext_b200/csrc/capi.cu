@@ -17,6 +17,7 @@ cudaError_t m_launch(const MPlan&, const KernelArgs&, cudaStream_t);  // recconv
 bool m_static_geometry(const MPlan&);
 struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ, staged, offW, kc; };  // ffn_mma.cu
 int ffn_make_plan(FfnPlan&, int B, int C, int HID, int HW, int dtype);
+int dwdown_launch(int B, int C, int H, int W, int dtype, const void* x, const float* w, const float* b, void* out, cudaStream_t stream, cudaError_t* err);
 cudaError_t ffn_launch(const FfnPlan&, const void* y, const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
                        cudaStream_t stream);
 template <int K, typename T, bool BWD> cudaError_t w_launch(const WPlan&, const KernelArgs&, cudaStream_t);
@@ -296,6 +297,18 @@ RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const v
                        void* y, void* stream) {
     if (zH < 1 || zW < 1) return fail(RECNEXT_EINVAL, "recattn_up_forward: bad z size %dx%d", zH, zW);
     return recattn_launch(d, 2, w, b, x, z, zH, zW, y, stream, "recattn_up_forward");
+}
+
+RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w, const float* b,
+                           void* out, void* stream) {
+    if (B < 0 || C < 1 || H < 1 || W < 1) return fail(RECNEXT_EINVAL, "recnext_dwdown_forward: bad shape [%d,%d,%d,%d]", B, C, H, W);
+    if (B == 0) return RECNEXT_OK;
+    if (!x || !w || !b || !out) return fail(RECNEXT_EINVAL, "recnext_dwdown_forward: null tensor");
+    cudaError_t e = cudaSuccess;
+    const int rc = dwdown_launch(B, C, H, W, dtype, x, w, b, out, (cudaStream_t)stream, &e);
+    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_dwdown_forward: 16-bit activations only, and a %dx%d plane must fit in shared memory", H, W);
+    if (rc) return fail(RECNEXT_ECUDA, "recnext_dwdown_forward: %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
 }
 
 RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_t HW, int32_t dtype, const void* y, const void* x,

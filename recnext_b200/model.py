@@ -161,6 +161,26 @@ class RecNextStem(nn.Module):
         return self.stem(x)
 
 
+def dwdown_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """norm(token_mixer(x)) of a Downsample block: depthwise 7x7 stride-2 conv, channel multiplier 2, BatchNorm folded into (w, b)
+    (reference model/recnext.py:137-138,145) as one sm_100a kernel (``recnext_dwdown_forward``).  16-bit CUDA tensors only."""
+    if not x.is_cuda:
+        raise RuntimeError("recnext_b200.dwdown_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if x.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("dwdown_forward: 16-bit activations (bfloat16 / float16) only")
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    if tuple(w.shape) != (2 * C, 1, 7, 7) or tuple(b.shape) != (2 * C,):
+        raise ValueError(f"dwdown_forward: w {tuple(w.shape)} / b {tuple(b.shape)} do not match x {tuple(x.shape)}")
+    out = torch.empty(B, 2 * C, (H - 1) // 2 + 1, (W - 1) // 2 + 1, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        ev = _timing_start()
+        N.check(N.lib().recnext_dwdown_forward(B, C, H, W, _DTYPES[x.dtype], x.data_ptr(), w.float().contiguous().data_ptr(),
+                                               b.float().contiguous().data_ptr(), out.data_ptr(), _stream(x)), "recnext_dwdown_forward")
+        _timing_stop(ev, (x.numel() + out.numel()) * x.element_size(), ("dwdown",) + tuple(x.shape))
+    return out
+
+
 def _ffn_shape_ok(block: nn.Module, x: torch.Tensor) -> bool:
     """Does this block (eval mode, ConvNorms folded) take the fused channel-mixer kernel for input x?"""
     if block.training or not x.is_cuda or not FUSED_FFN or torch.jit.is_tracing():
@@ -249,10 +269,29 @@ class Downsample(nn.Module):
 
     def train(self, mode: bool = True):
         self._ffn_cache = None
+        self._dw_cache = None
         return super().train(mode)
 
+    def _dw_params(self, device):
+        c = getattr(self, "_dw_cache", None)
+        if c is None or c[0] != device:
+            conv, bn = self.token_mixer, self.norm
+            with torch.no_grad():
+                s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+                t = (bn.bias - s * bn.running_mean).float()
+                w = (conv.weight.float() * s.view(-1, 1, 1, 1)).contiguous()
+                b = (s * conv.bias.float() + t).contiguous() if conv.bias is not None else t.contiguous()
+            c = (device, (w, b))
+            self._dw_cache = c
+        return c[1]
+
     def forward(self, x):
-        x = self.norm(self.token_mixer(x))
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        if (not self.training and x.is_cuda and FUSED_FFN and dt in (torch.bfloat16, torch.float16) and not torch.jit.is_tracing()
+                and (x.shape[2] + 8) * (x.shape[3] + 9) * 4 + 448 <= 227 * 1024):
+            x = dwdown_forward(x.to(dt), *self._dw_params(x.device))   # norm(token_mixer(x)): one kernel, BatchNorm folded
+        else:
+            x = self.norm(self.token_mixer(x))
         if _ffn_shape_ok(self, x):
             # x + mlp(x) (model/recnext.py:145-146) as the same fused kernel: the mixer input is also the residual
             c = getattr(self, "_ffn_cache", None)

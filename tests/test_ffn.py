@@ -95,3 +95,49 @@ def test_block_with_fused_ffn_matches_library_path(monkeypatch):
     assert y_fused.dtype == torch.bfloat16
     assert rel_err(y_fused.float().cpu().numpy(), ref32.cpu().numpy()) < TOL_BF16
     assert rel_err(y_lib.float().cpu().numpy(), ref32.cpu().numpy()) < TOL_BF16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 64, 56, 56), (3, 128, 28, 28), (3, 256, 14, 14), (2, 40, 56, 56), (2, 6, 9, 13), (1, 3, 25, 42), (2, 4, 7, 7)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_dwdown_kernel_vs_torch(shape, dtype):
+    """Downsample token mixer (depthwise 7x7 stride 2, multiplier 2, + bias; reference model/recnext.py:137-138) vs F.conv2d"""
+    from recnext_b200.model import dwdown_forward
+
+    B, C, H, W = shape
+    torch.manual_seed(C + H)
+    x = torch.randn(shape, device="cuda").to(dtype)
+    w = torch.randn(2 * C, 1, 7, 7, device="cuda") / 7.0
+    b = 0.1 * torch.randn(2 * C, device="cuda")
+    out = dwdown_forward(x, w, b)
+    ref = F.conv2d(x.float(), w, b, stride=2, padding=3, groups=C)
+    assert out.shape == ref.shape
+    assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < (TOL_BF16 if dtype == torch.bfloat16 else 4e-3)
+
+
+@pytest.mark.gpu
+def test_downsample_block_fused_matches_library_path(monkeypatch):
+    import recnext_b200.model as M
+
+    torch.manual_seed(3)
+    blk = M.Downsample(64, 2)
+    g = torch.Generator().manual_seed(1)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(0.3 * torch.randn(m.num_features, generator=g)); m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(0.7 + 0.6 * torch.rand(m.num_features, generator=g)); m.bias.data.copy_(0.2 * torch.randn(m.num_features, generator=g))
+    blk.eval()
+    M.replace_batchnorm(blk)
+    blk.cuda()
+    x = torch.randn(4, 64, 56, 56, device="cuda")
+    with torch.no_grad():
+        ref = blk.norm(blk.token_mixer(x))
+        ref = ref + blk.channel_mixer(ref)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = blk(x)
+            monkeypatch.setattr(M, "FUSED_FFN", False)
+            y_lib = blk(x)
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (4, 128, 28, 28)
+    assert rel_err(y.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
+    assert rel_err(y_lib.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
