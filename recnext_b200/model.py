@@ -11,7 +11,7 @@ everything except the token mixer is plain PyTorch (out of scope for the CUDA wo
 """
 from __future__ import annotations
 
-from typing import Callable, Sequence
+from typing import Callable, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -181,6 +181,28 @@ def dwdown_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.T
     return out
 
 
+def _fold_mlp(fc1: nn.Conv2d, fc2: nn.Conv2d, dtype, bn: Optional[nn.BatchNorm2d] = None):
+    """(w1, b1, w2, b2) for ffn_forward from the two folded 1x1 convs of an `mlp`; an eval-mode BatchNorm in front of it is folded
+    into (w1, b1): W1 (s*y + t) + b1 = (W1 diag(s)) y + (b1 + W1 t).  The hidden width is zero-padded to a multiple of 32
+    (gelu(0) = 0 meets zero columns of W2), so e.g. the A-series' 1.875 ratio (120 hidden channels at C = 64) is served too."""
+    with torch.no_grad():
+        w1 = fc1.weight.float().view(fc1.out_channels, fc1.in_channels)
+        w2 = fc2.weight.float().view(fc2.out_channels, fc2.in_channels)
+        b1, b2 = fc1.bias.float(), fc2.bias.float()
+        if bn is not None:
+            s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+            t = (bn.bias - s * bn.running_mean).float()
+            b1 = b1 + w1 @ t
+            w1 = w1 * s.view(1, -1)
+        hid = w1.shape[0]
+        pad = (-hid) % 32
+        if pad:
+            w1 = torch.cat([w1, w1.new_zeros(pad, w1.shape[1])], 0)
+            b1 = torch.cat([b1, b1.new_zeros(pad)], 0)
+            w2 = torch.cat([w2, w2.new_zeros(w2.shape[0], pad)], 1)
+        return w1.to(dtype).contiguous(), b1.contiguous(), w2.to(dtype).contiguous(), b2.contiguous()
+
+
 def _ffn_shape_ok(block: nn.Module, x: torch.Tensor) -> bool:
     """Does this block (eval mode, ConvNorms folded) take the fused channel-mixer kernel for input x?"""
     if block.training or not x.is_cuda or not FUSED_FFN or torch.jit.is_tracing():
@@ -191,9 +213,9 @@ def _ffn_shape_ok(block: nn.Module, x: torch.Tensor) -> bool:
     if not isinstance(block.channel_mixer[1], nn.GELU) or getattr(block.channel_mixer[1], "approximate", "none") != "none":
         return False
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
-    if x.dtype != dt and not isinstance(block, MetaNeXtBlock):
+    if x.dtype != dt and isinstance(block, Downsample):
         return False
-    C, hid, HW = fc1.in_channels, fc1.out_channels, x.shape[2] * x.shape[3]
+    C, hid, HW = fc1.in_channels, (fc1.out_channels + 31) // 32 * 32, x.shape[2] * x.shape[3]
     # measured on B200 (tools/ffn_check.py, batch 256; kernel vs the library path it replaces): [64, 56x56] 0.28 vs 0.78 ms,
     # [128, 28x28] 0.24 vs 0.41 ms, [256, 14x14] 0.24 vs 0.34 ms (weights staged through shared memory: 192 <= C <= 256 and
     # C % 32 == 0; [320, 14x14] 0.45 vs 0.43 ms is not worth it yet).  Narrow stages with small images stay on the library
@@ -219,21 +241,12 @@ class MetaNeXtBlock(nn.Module):
         return super().train(mode)
 
     def _ffn_params(self, dtype, device):
-        """(w1, b1, w2, b2) of the fused channel mixer: eval-mode BatchNorm `norm` folded into the first 1x1 conv.
-        y -> s*y + t  =>  W1 (s*y + t) + b1 = (W1 diag(s)) y + (b1 + W1 t)."""
+        """(w1, b1, w2, b2) of the fused channel mixer, eval-mode BatchNorm `norm` folded in; cached until train() is called"""
         c = getattr(self, "_ffn_cache", None)
-        if c is not None and c[0] == (dtype, device):
-            return c[1]
-        fc1, fc2, bn = self.channel_mixer[0], self.channel_mixer[2], self.norm
-        with torch.no_grad():
-            s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
-            t = (bn.bias - s * bn.running_mean).float()
-            w1 = fc1.weight.float().view(fc1.out_channels, fc1.in_channels)
-            w2 = fc2.weight.float().view(fc2.out_channels, fc2.in_channels)
-            params = ((w1 * s.view(1, -1)).to(dtype).contiguous(), (fc1.bias.float() + w1 @ t).contiguous(),
-                      w2.to(dtype).contiguous(), fc2.bias.float().contiguous())
-        self._ffn_cache = ((dtype, device), params)
-        return params
+        if c is None or c[0] != (dtype, device):
+            c = ((dtype, device), _fold_mlp(self.channel_mixer[0], self.channel_mixer[2], dtype, self.norm))
+            self._ffn_cache = c
+        return c[1]
 
     def _ffn_eligible(self, x) -> bool:
         return _ffn_shape_ok(self, x)
@@ -256,7 +269,18 @@ class MetaNeXtBlockA(nn.Module):
         self.channel_mixer = mlp(dim, dim * mlp_ratio, act_layer)
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
+    def train(self, mode: bool = True):
+        self._ffn_cache = None
+        return super().train(mode)
+
     def forward(self, x):
+        if _ffn_shape_ok(self, x):
+            y = self.token_mixer(x)
+            c = getattr(self, "_ffn_cache", None)
+            if c is None or c[0] != (y.dtype, y.device):
+                c = ((y.dtype, y.device), _fold_mlp(self.channel_mixer[0], self.channel_mixer[2], y.dtype))
+                self._ffn_cache = c
+            return ffn_forward(y, x.to(y.dtype), *c[1])
         return x + self.drop_path(self.channel_mixer(self.token_mixer(x)))
 
 
@@ -296,10 +320,7 @@ class Downsample(nn.Module):
             # x + mlp(x) (model/recnext.py:145-146) as the same fused kernel: the mixer input is also the residual
             c = getattr(self, "_ffn_cache", None)
             if c is None or c[0] != (x.dtype, x.device):
-                fc1, fc2 = self.channel_mixer[0], self.channel_mixer[2]
-                with torch.no_grad():
-                    c = ((x.dtype, x.device), (fc1.weight.view(fc1.out_channels, -1).to(x.dtype).contiguous(), fc1.bias.float().contiguous(),
-                                               fc2.weight.view(fc2.out_channels, -1).to(x.dtype).contiguous(), fc2.bias.float().contiguous()))
+                c = ((x.dtype, x.device), _fold_mlp(self.channel_mixer[0], self.channel_mixer[2], x.dtype))
                 self._ffn_cache = c
             return ffn_forward(x, x, *c[1])
         return x + self.channel_mixer(x)
