@@ -167,3 +167,42 @@ def test_fma_path_still_serves_16bit_activations():
     y_mma = R.recconv_forward(x, ws, None, 5, 4, "bilinear")
     # FMA path keeps fp32 intermediates, the tensor-core path rounds like the reference: both within the bar of each other
     assert rel_err(y_mma.float().cpu().numpy(), y_fma.float().numpy()) < TOL_BF16
+
+
+def test_kernels_are_cuda_graph_capturable():
+    """The C ABI promises stream-ordered calls with no allocation and no synchronisation (include/recnext_b200.h): a RecNeXt block
+    (RecConv forward + fused channel mixer) and the RecAttn2d pieces are captured in a CUDA graph and replayed on new data."""
+    import recnext_b200 as R
+    from recnext_b200.model import ffn_forward
+
+    torch.manual_seed(21)
+    C, L = 64, 4
+    ws, _ = _params(C, L, False, 5)
+    w1 = (torch.randn(2 * C, C, device=DEV) * C ** -0.5).bfloat16(); w2 = (torch.randn(C, 2 * C, device=DEV) * (2 * C) ** -0.5).bfloat16()
+    b1 = 0.1 * torch.randn(2 * C, device=DEV); b2 = 0.1 * torch.randn(C, device=DEV)
+    wd = torch.randn(C, 1, 5, 5, device=DEV) * 0.2; bd = 0.1 * torch.randn(C, device=DEV)
+    x = torch.randn(8, C, 56, 56, device=DEV).bfloat16()
+
+    def block(inp):
+        y = R.recconv_forward(inp, ws, None, 5, L, "bilinear")
+        o = ffn_forward(y, inp, w1, b1, w2, b2)
+        low = R.recattn_down_forward(o, wd, bd)
+        return R.recattn_up_forward(o, low, wd, bd, "nearest")
+
+    ref1 = block(x)                       # eager (also warms every lazily configured kernel attribute)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = block(x)
+    torch.cuda.current_stream().wait_stream(s)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref1)
+    x2 = torch.randn_like(x)
+    ref2 = block(x2)
+    x.copy_(x2)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref2)
