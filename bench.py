@@ -139,6 +139,65 @@ def run_reference(args, rank: int):
     print(json.dumps(out), flush=True)
 
 
+def run_train(args, rank: int, local_rank: int, world: int):
+    """Training step of BASELINE.json configs[2] (RecNeXt-M5 by default via --model): forward + backward + AdamW on a synthetic
+    batch, bf16 autocast, one process per GPU, DDP gradient all-reduce over NCCL (the only collective of the path).
+    RecConv2d runs the sm_100a kernels in both directions (tensor-core forward, fused FMA backward); the rest is PyTorch."""
+    import torch
+    import torch.nn.functional as F
+
+    from recnext_b200 import dist as D
+    from recnext_b200 import recconv as RC
+    from recnext_b200.model import create_model
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    D.init("nccl", dev)
+    torch.backends.cudnn.benchmark = True
+    batch = args.batch or 128
+    torch.manual_seed(0)                      # identical initial weights on every rank (DDP also broadcasts them)
+    net = create_model(MODEL, drop_path=0.0).to(dev).train()
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05)
+    torch.manual_seed(1 + rank)
+    x = torch.randn(batch, 3, RES, RES, device=dev)
+    tgt = torch.randint(0, 1000, (batch,), device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(model(x).float(), tgt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    D.barrier(dev)
+    RC.timing_begin()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss = step()
+    b.record()
+    D.barrier(dev)
+    ms = D.max_over_ranks(a.elapsed_time(b), dev)
+    fwd = RC.timing_end()
+    loss_v = float(loss.detach())
+    if rank == 0:
+        tag = MODEL.split("_")[1].upper()
+        print(json.dumps({
+            "metric": f"RecNeXt-{tag} training images/sec (fwd+bwd+AdamW, batch {batch}/GPU, 224x224, bf16 autocast)", "value": D.job_throughput(batch, world, args.steps, ms),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"RecNeXt-{tag} training step, batch {batch}/GPU at 224x224 bf16 autocast, AdamW (BASELINE.json configs[2])", "model": MODEL,
+                       "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"ddp x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU"},
+            "gpu_launches": len(fwd), "final_loss": loss_v,
+            "recconv_forward_share_of_step": round(sum(r["ms"] for r in fwd) / ms, 4),
+        }), flush=True)
+    D.finalize()
+
+
 def recconv_microbench(torch, R, peak):
     """RecConv fwd+bwd achieved GB/s on the four M3 stage shapes (batch 256, bf16): the second half of
     BASELINE.json's metric.  Algorithmic bytes: fwd 2*N*e, bwd 3*N*e.  L2 flushed per launch."""
@@ -178,6 +237,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--model", default=MODEL, help="recnext_m0..m5 / recnext_a0..a5 (default: the metric's recnext_m3)")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE.json configs[2]: training step (fwd + bwd + AdamW, bf16 autocast, DDP over NCCL when launched with torchrun) "
+                         "instead of inference; --batch images per GPU (default 128)")
+    ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--memory-format", default="contiguous", choices=["contiguous", "channels_last"],
                     help="memory format of the model around RecConv2d (the RecConv kernels always work on NCHW planes)")
     args = ap.parse_args()
@@ -190,6 +253,9 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.train:
+        run_train(args, rank, local_rank, world)
+        return
 
     import torch
 
