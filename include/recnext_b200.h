@@ -131,6 +131,17 @@ RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_
 RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w,
                                        const float* b, void* out, void* stream);
 
+/*
+ * Contraction core of the A-series linear attention: replaces everything between the `qk` ConvNorm and
+ * the final `+ self.pe(v)` of LinearAttention1.forward (model/recattn.py:21-28) / LinearAttention2.forward (:44-51) — the two
+ * are the same function:   q, k = elu(qk) + 1;  out = q^T (k v^T / n) / (q^T mean(k) + 1e-6)  (+ pe), per image and head.
+ * qk: [B, 2*dim, n] (output of the grouped 1x1 ConvNorm, pre-activation; q = first dim channels), v, pe, out: [B, dim, n]
+ * (= NCHW with n = h*w) in dtype (RECNEXT_BF16 | RECNEXT_F16); pe may be NULL.  head_dim = dim / heads in {16,20,24,28,32,40}
+ * (every RecNeXt-A model), else RECNEXT_EUNSUPPORTED.  Inference entry point.
+ */
+RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* qk, const void* v,
+                                        const void* pe, void* out, void* stream);
+
 /* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);
 

@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
     L.recattn_up_forward.restype = ctypes.c_int
     L.recattn_up_forward.argtypes = [ctypes.POINTER(RecConvDesc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    L.recnext_linattn_forward.restype = ctypes.c_int
+    L.recnext_linattn_forward.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 5
     L.recnext_dwdown_forward.restype = ctypes.c_int
     L.recnext_dwdown_forward.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 5
     L.recnext_ffn_forward.restype = ctypes.c_int
@@ -86,5 +88,5 @@ def check(rc: int, what: str) -> None:
 
 EXPORTS = [
     "recnext_abi_version", "recnext_last_error", "recconv_forward", "recconv_backward_workspace_bytes", "recconv_backward",
-    "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward", "recnext_ffn_forward", "recnext_dwdown_forward",
+    "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward", "recnext_ffn_forward", "recnext_dwdown_forward", "recnext_linattn_forward",
 ]

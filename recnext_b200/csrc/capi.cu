@@ -17,6 +17,7 @@ cudaError_t m_launch(const MPlan&, const KernelArgs&, cudaStream_t);  // recconv
 bool m_static_geometry(const MPlan&);
 struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ, staged, offW, kc; };  // ffn_mma.cu
 int ffn_make_plan(FfnPlan&, int B, int C, int HID, int HW, int dtype);
+int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* qk, const void* v, const void* pe, void* out, cudaStream_t stream, cudaError_t* err);
 int dwdown_launch(int B, int C, int H, int W, int dtype, const void* x, const float* w, const float* b, void* out, cudaStream_t stream, cudaError_t* err);
 cudaError_t ffn_launch(const FfnPlan&, const void* y, const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
                        cudaStream_t stream);
@@ -297,6 +298,18 @@ RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const v
                        void* y, void* stream) {
     if (zH < 1 || zW < 1) return fail(RECNEXT_EINVAL, "recattn_up_forward: bad z size %dx%d", zH, zW);
     return recattn_launch(d, 2, w, b, x, z, zH, zW, y, stream, "recattn_up_forward");
+}
+
+RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* qk, const void* v, const void* pe,
+                            void* out, void* stream) {
+    if (B < 0 || dim < 1 || heads < 1 || n < 1) return fail(RECNEXT_EINVAL, "recnext_linattn_forward: bad shape [%d,%d,%d] heads %d", B, dim, n, heads);
+    if (B == 0) return RECNEXT_OK;
+    if (!qk || !v || !out) return fail(RECNEXT_EINVAL, "recnext_linattn_forward: null tensor");
+    cudaError_t e = cudaSuccess;
+    const int rc = linattn_launch(B, dim, heads, n, dtype, qk, v, pe, out, (cudaStream_t)stream, &e);
+    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_linattn_forward: 16-bit activations and head_dim in {16,20,24,28,32,40} only (dim %d, heads %d)", dim, heads);
+    if (rc) return fail(RECNEXT_ECUDA, "recnext_linattn_forward: %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
 }
 
 RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w, const float* b,

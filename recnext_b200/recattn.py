@@ -10,14 +10,16 @@ What runs where:
   * the two plane-independent, memory-bound pieces — the stride-2 depthwise conv and the fused
     ``conv(x + interpolate(z))`` tail — run in the hand-written sm_100a tensor-core kernels behind
     ``recattn_down_forward`` / ``recattn_up_forward`` (include/recnext_b200.h), BatchNorm folded into (w, b);
-  * the linear attention in between mixes channels (1x1 grouped conv, d x d contractions): plain batched GEMMs,
-    left to the library (torch.matmul / cuBLAS) exactly as the reference writes them (model/recattn.py:16-51).
+  * the linear attention in between: its contraction chain (elu + 1, k v^T, mean(k), q^T kv / (q^T mean(k) + 1e-6), + pe;
+    model/recattn.py:21-28, 44-51) is one more kernel (``recnext_linattn_forward``); its two ConvNorms (grouped 1x1 ``qk``,
+    depthwise 3x3 ``pe``) stay library convs.  Outside eval mode / 16-bit CUDA the reference's op chain runs as written.
 Inference only for now (16-bit CUDA activations, eval mode): training through the custom kernels needs their
 backward, which is not built yet, so ``forward`` raises in training mode instead of silently falling back.
 """
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -136,6 +138,37 @@ def _wb(m):
     return m.weight, m.bias
 
 
+def linattn_forward(qk: torch.Tensor, v: torch.Tensor, pe: Optional[torch.Tensor], num_heads: int) -> torch.Tensor:
+    """q, k = elu(qk) + 1;  out = q^T (k v^T / n) / (q^T mean(k) + 1e-6) (+ pe) per image and head — everything between the
+    ``qk`` ConvNorm and the final add of LinearAttention1/2.forward (reference model/recattn.py:21-28, :44-51) as ONE sm_100a
+    kernel (``recnext_linattn_forward``).  qk: [B, 2*dim, h, w] pre-activation, v / pe: [B, dim, h, w]; 16-bit CUDA tensors."""
+    if not qk.is_cuda:
+        raise RuntimeError("recnext_b200.linattn_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if qk.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError(f"linattn_forward: 16-bit activations (bfloat16 / float16) only, got {qk.dtype}")
+    qk, v = qk.contiguous(), v.to(qk.dtype).contiguous()
+    pe = None if pe is None else pe.to(qk.dtype).contiguous()
+    B, dim, H, W = v.shape
+    if qk.shape[1] != 2 * dim or tuple(qk.shape[2:]) != (H, W):
+        raise ValueError(f"linattn_forward: qk {tuple(qk.shape)} does not match v {tuple(v.shape)}")
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        ev = _timing_start()
+        N.check(N.lib().recnext_linattn_forward(B, dim, num_heads, H * W, _DTYPES[qk.dtype], qk.data_ptr(), v.data_ptr(),
+                                                None if pe is None else pe.data_ptr(), out.data_ptr(), _stream(v)), "recnext_linattn_forward")
+        _timing_stop(ev, (qk.numel() + 2 * v.numel() + (0 if pe is None else pe.numel())) * v.element_size(), ("linattn",) + tuple(v.shape))
+    return out
+
+
+LINATTN_HEAD_DIMS = (16, 20, 24, 28, 32, 40)
+
+
+def _linattn_eligible(mod: nn.Module, x: torch.Tensor) -> bool:
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+    return (not mod.training and x.is_cuda and dt in (torch.bfloat16, torch.float16) and mod.head_dim in LINATTN_HEAD_DIMS
+            and os.environ.get("RECNEXT_LINATTN", "1") != "0" and not torch.jit.is_tracing())
+
+
 class LinearAttention1(nn.Module):
     """model/recattn.py:8-28 — kv formulation, O(n d^2)"""
 
@@ -147,6 +180,8 @@ class LinearAttention1(nn.Module):
         self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim)
 
     def forward(self, x):
+        if _linattn_eligible(self, x):   # the whole contraction chain as one kernel; the two ConvNorms stay library convs
+            return linattn_forward(self.qk(x), x, self.pe(x), self.num_heads)
         b, c, h, w = x.shape
         n = h * w
         s = n ** -0.5
@@ -169,6 +204,8 @@ class LinearAttention2(nn.Module):
         self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim)
 
     def forward(self, x):
+        if _linattn_eligible(self, x):   # same function as LinearAttention1 (model/recattn.py:56-57): same kernel
+            return linattn_forward(self.qk(x), x, self.pe(x), self.num_heads)
         b, c, h, w = x.shape
         n = h * w
         s = n ** -0.5

@@ -125,3 +125,55 @@ def test_cuda_full_size_a3_stage_shapes():
         y = recattn_up_forward(x, zz, w, b, "nearest")
         ref = F.conv2d(x.float() + F.interpolate(zz.float(), size=(H, H), mode="nearest"), w, b, padding=2, groups=C)
         assert rel_err(y.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
+def test_cuda_linear_attention_kernel_against_reference(path):
+    """recnext_linattn_forward (LinearAttention1/2 contraction core, model/recattn.py:21-28,44-51) against the reference's z,
+    fed with the reference's own low-resolution input (fixture `low`); the two ConvNorms around it run as library convs."""
+    from recnext_b200.recattn import linattn_forward
+
+    z, meta, sd = _load(path)
+    m = _module(meta, sd).cuda()
+    from recnext_b200.recattn import LINATTN_HEAD_DIMS
+
+    la = m.down[1]
+    low = torch.from_numpy(z["low"]).cuda()
+    if la.head_dim not in LINATTN_HEAD_DIMS:   # (toy fixture: head_dim 4) the module keeps the reference's op chain, the kernel refuses
+        with pytest.raises(RuntimeError, match="head_dim"):
+            linattn_forward(la.qk(low).bfloat16(), low.bfloat16(), None, la.num_heads)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            assert rel_err(la(low).float().cpu().numpy(), z["z"]) < TOL_BF16
+        return
+    with torch.no_grad():
+        qk_pre = la.qk(low)
+        pe = la.pe(low)
+        out = linattn_forward(qk_pre.bfloat16(), low.bfloat16(), pe.bfloat16(), la.num_heads)
+    assert rel_err(out.float().cpu().numpy(), z["z"]) < TOL_BF16
+    # and through the module switch (eval, autocast): same bar
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out2 = la(low)
+    assert out2.dtype == torch.bfloat16
+    assert rel_err(out2.float().cpu().numpy(), z["z"]) < TOL_BF16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,heads,n", [(16, 2, 5), (20, 2, 784), (24, 4, 196), (28, 8, 49), (32, 16, 16), (40, 2, 130)])
+def test_cuda_linear_attention_head_dims(d, heads, n):
+    """every head_dim of the A-series (model/recattn.py:380-426) against the reference formula in fp32"""
+    from recnext_b200.recattn import linattn_forward
+
+    torch.manual_seed(d + n)
+    B, dim = 3, d * heads
+    qk = torch.randn(B, 2 * dim, 1, n, device="cuda").bfloat16(); v = torch.randn(B, dim, 1, n, device="cuda").bfloat16()
+    pe = torch.randn(B, dim, 1, n, device="cuda").bfloat16()
+    out = linattn_forward(qk, v, pe, heads)
+    a = F.elu(qk.float()) + 1.0
+    q, k = a.view(B, 2, heads, d, n).unbind(1)
+    vv = v.float().view(B, heads, d, n)
+    s = n ** -0.5
+    q_t = q.transpose(-1, -2)
+    kvm = (k * s) @ (vv.transpose(-1, -2) * s)
+    ref = (q_t @ kvm / (q_t @ k.mean(dim=-1, keepdim=True) + 1e-6)).transpose(-1, -2).reshape(B, dim, 1, n) + pe.float()
+    assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
