@@ -125,7 +125,8 @@ RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_
  * Token mixer of a `Downsample` block: depthwise 7x7 stride-2 conv with channel multiplier 2 and the
  * eval-mode BatchNorm that follows it folded into (w, b) by the caller — replaces
  *     self.norm(self.token_mixer(x))      model/recnext.py:137-138,145
- * x: [B, C, H, W], out: [B, 2C, (H-1)/2+1, (W-1)/2+1] in dtype (RECNEXT_BF16 | RECNEXT_F16); w: [2C, 1, 7, 7] fp32, b: [2C] fp32.
+ * x: [B, C, H, W], out: [B, 2C, (H-1)/2+1, (W-1)/2+1] in dtype (RECNEXT_F32 | RECNEXT_BF16 | RECNEXT_F16; fp32 arithmetic);
+ * w: [2C, 1, 7, 7] fp32, b: [2C] fp32.
  * Inference entry point.  RECNEXT_EUNSUPPORTED if a padded fp32 plane does not fit in shared memory.
  */
 RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w,
@@ -136,7 +137,8 @@ RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t 
  * the final `+ self.pe(v)` of LinearAttention1.forward (model/recattn.py:21-28) / LinearAttention2.forward (:44-51) — the two
  * are the same function:   q, k = elu(qk) + 1;  out = q^T (k v^T / n) / (q^T mean(k) + 1e-6)  (+ pe), per image and head.
  * qk: [B, 2*dim, n] (output of the grouped 1x1 ConvNorm, pre-activation; q = first dim channels), v, pe, out: [B, dim, n]
- * (= NCHW with n = h*w) in dtype (RECNEXT_BF16 | RECNEXT_F16); pe may be NULL.  head_dim = dim / heads in {16,20,24,28,32,40}
+ * (= NCHW with n = h*w) in dtype (RECNEXT_F32 | RECNEXT_BF16 | RECNEXT_F16; fp32 accumulation throughout); pe may be NULL.
+ * head_dim = dim / heads in {4,8,16,20,24,28,32,40}
  * (every RecNeXt-A model), else RECNEXT_EUNSUPPORTED.  Inference entry point.
  */
 RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* qk, const void* v,

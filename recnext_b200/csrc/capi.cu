@@ -307,7 +307,7 @@ RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, i
     if (!qk || !v || !out) return fail(RECNEXT_EINVAL, "recnext_linattn_forward: null tensor");
     cudaError_t e = cudaSuccess;
     const int rc = linattn_launch(B, dim, heads, n, dtype, qk, v, pe, out, (cudaStream_t)stream, &e);
-    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_linattn_forward: 16-bit activations and head_dim in {16,20,24,28,32,40} only (dim %d, heads %d)", dim, heads);
+    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_linattn_forward: head_dim in {4,8,16,20,24,28,32,40} only (dim %d, heads %d)", dim, heads);
     if (rc) return fail(RECNEXT_ECUDA, "recnext_linattn_forward: %s", cudaGetErrorString(e));
     return RECNEXT_OK;
 }
@@ -319,7 +319,7 @@ RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t 
     if (!x || !w || !b || !out) return fail(RECNEXT_EINVAL, "recnext_dwdown_forward: null tensor");
     cudaError_t e = cudaSuccess;
     const int rc = dwdown_launch(B, C, H, W, dtype, x, w, b, out, (cudaStream_t)stream, &e);
-    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_dwdown_forward: 16-bit activations only, and a %dx%d plane must fit in shared memory", H, W);
+    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_dwdown_forward: a padded fp32 %dx%d plane must fit in shared memory", H, W);
     if (rc) return fail(RECNEXT_ECUDA, "recnext_dwdown_forward: %s", cudaGetErrorString(e));
     return RECNEXT_OK;
 }

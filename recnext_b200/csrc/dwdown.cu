@@ -16,9 +16,11 @@ namespace recnext {
 template <typename T> __device__ __forceinline__ float dd_to_f(T v);
 template <> __device__ __forceinline__ float dd_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <> __device__ __forceinline__ float dd_to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float dd_to_f<float>(float v) { return v; }
 template <typename T> __device__ __forceinline__ T dd_from_f(float v);
 template <> __device__ __forceinline__ __nv_bfloat16 dd_from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half dd_from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ float dd_from_f<float>(float v) { return v; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) recnext_dwdown_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
@@ -88,7 +90,7 @@ int dwdown_launch(int B, int C, int H, int W, int dtype, const void* x, const fl
     int pitch = W + 8;
     if ((pitch & 1) == 0) ++pitch;                       // odd pitch: the stride-2 window rows of neighbouring threads spread over the banks
     const size_t pbytes = (112 + (size_t)(H + 8) * pitch) * sizeof(float);
-    if (pbytes > 227 * 1024 || !(dtype == 1 || dtype == 2)) return 1;
+    if (pbytes > 227 * 1024 || dtype < 0 || dtype > 2) return 1;
     const int nblk = ((Wo + 1) / 2) * ((Ho + 1) / 2);
     int PP = 256 / nblk;                                 // planes per CTA: enough 2x2 blocks for every thread
     if (PP < 1) PP = 1;
@@ -100,11 +102,13 @@ int dwdown_launch(int B, int C, int H, int W, int dtype, const void* x, const fl
     if (!configured) {
         *err = cudaFuncSetAttribute(recnext_dwdown_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (*err == cudaSuccess) *err = cudaFuncSetAttribute(recnext_dwdown_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (*err == cudaSuccess) *err = cudaFuncSetAttribute(recnext_dwdown_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (*err != cudaSuccess) return 2;
         configured = 1;
     }
     const int grid = (int)((nplanes + PP - 1) / PP);
-    if (dtype == 1) recnext_dwdown_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)x, w, b, (__nv_bfloat16*)out, C, H, W, Ho, Wo, pitch, PP, nplanes);
+    if (dtype == 0) recnext_dwdown_kernel<float><<<grid, 256, smem, stream>>>((const float*)x, w, b, (float*)out, C, H, W, Ho, Wo, pitch, PP, nplanes);
+    else if (dtype == 1) recnext_dwdown_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)x, w, b, (__nv_bfloat16*)out, C, H, W, Ho, Wo, pitch, PP, nplanes);
     else recnext_dwdown_kernel<__half><<<grid, 256, smem, stream>>>((const __half*)x, w, b, (__half*)out, C, H, W, Ho, Wo, pitch, PP, nplanes);
     *err = cudaGetLastError();
     return *err == cudaSuccess ? 0 : 2;

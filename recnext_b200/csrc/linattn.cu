@@ -21,11 +21,13 @@ namespace recnext {
 template <typename T> __device__ __forceinline__ float la_to_f(T v);
 template <> __device__ __forceinline__ float la_to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <> __device__ __forceinline__ float la_to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float la_to_f<float>(float v) { return v; }
 template <typename T> __device__ __forceinline__ T la_from_f(float v);
 template <> __device__ __forceinline__ __nv_bfloat16 la_from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half la_from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ float la_from_f<float>(float v) { return v; }
 
-__device__ __forceinline__ float la_elu1(float v) { return v > 0.f ? v + 1.f : __expf(v); }   // elu(v) + 1
+__device__ __forceinline__ float la_elu1(float v) { return v > 0.f ? v + 1.f : expf(v); }   // elu(v) + 1 (expm1(v) + 1 = exp(v))
 
 template <typename T, int D>
 __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __restrict__ qk, const T* __restrict__ v, const T* __restrict__ pe,
@@ -152,7 +154,7 @@ static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* qk, c
     const int grid = B * heads;
 #define LA_CASE(DD) case DD: recnext_linattn_kernel<T, DD><<<grid, 256, 0, s>>>((const T*)qk, (const T*)v, (const T*)pe, (T*)out, heads, n); break;
     switch (d) {
-        LA_CASE(16) LA_CASE(20) LA_CASE(24) LA_CASE(28) LA_CASE(32) LA_CASE(40)
+        LA_CASE(4) LA_CASE(8) LA_CASE(16) LA_CASE(20) LA_CASE(24) LA_CASE(28) LA_CASE(32) LA_CASE(40)
         default: return cudaErrorInvalidValue;
     }
 #undef LA_CASE
@@ -161,10 +163,11 @@ static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* qk, c
 
 // 0 ok, 1 unsupported head_dim / dtype, 2 CUDA error in *err
 int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* qk, const void* v, const void* pe, void* out, cudaStream_t stream, cudaError_t* err) {
-    if (heads < 1 || dim % heads != 0 || !(dtype == 1 || dtype == 2)) return 1;
+    if (heads < 1 || dim % heads != 0 || dtype < 0 || dtype > 2) return 1;
     const int d = dim / heads;
-    if (!(d == 16 || d == 20 || d == 24 || d == 28 || d == 32 || d == 40)) return 1;
-    *err = dtype == 1 ? la_launch_t<__nv_bfloat16>(B, heads, d, n, qk, v, pe, out, stream) : la_launch_t<__half>(B, heads, d, n, qk, v, pe, out, stream);
+    if (!(d == 4 || d == 8 || d == 16 || d == 20 || d == 24 || d == 28 || d == 32 || d == 40)) return 1;
+    *err = dtype == 0 ? la_launch_t<float>(B, heads, d, n, qk, v, pe, out, stream)
+         : dtype == 1 ? la_launch_t<__nv_bfloat16>(B, heads, d, n, qk, v, pe, out, stream) : la_launch_t<__half>(B, heads, d, n, qk, v, pe, out, stream);
     return *err == cudaSuccess ? 0 : 2;
 }
 

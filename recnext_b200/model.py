@@ -163,11 +163,11 @@ class RecNextStem(nn.Module):
 
 def dwdown_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """norm(token_mixer(x)) of a Downsample block: depthwise 7x7 stride-2 conv, channel multiplier 2, BatchNorm folded into (w, b)
-    (reference model/recnext.py:137-138,145) as one sm_100a kernel (``recnext_dwdown_forward``).  16-bit CUDA tensors only."""
+    (reference model/recnext.py:137-138,145) as one sm_100a kernel (``recnext_dwdown_forward``).  CUDA tensors, fp32 or 16-bit."""
     if not x.is_cuda:
         raise RuntimeError("recnext_b200.dwdown_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
-    if x.dtype not in (torch.bfloat16, torch.float16):
-        raise TypeError("dwdown_forward: 16-bit activations (bfloat16 / float16) only")
+    if x.dtype not in _DTYPES:
+        raise TypeError("dwdown_forward: float32 / bfloat16 / float16 only")
     x = x.contiguous()
     B, C, H, W = x.shape
     if tuple(w.shape) != (2 * C, 1, 7, 7) or tuple(b.shape) != (2 * C,):

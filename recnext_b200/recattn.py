@@ -141,11 +141,11 @@ def _wb(m):
 def linattn_forward(qk: torch.Tensor, v: torch.Tensor, pe: Optional[torch.Tensor], num_heads: int) -> torch.Tensor:
     """q, k = elu(qk) + 1;  out = q^T (k v^T / n) / (q^T mean(k) + 1e-6) (+ pe) per image and head — everything between the
     ``qk`` ConvNorm and the final add of LinearAttention1/2.forward (reference model/recattn.py:21-28, :44-51) as ONE sm_100a
-    kernel (``recnext_linattn_forward``).  qk: [B, 2*dim, h, w] pre-activation, v / pe: [B, dim, h, w]; 16-bit CUDA tensors."""
+    kernel (``recnext_linattn_forward``).  qk: [B, 2*dim, h, w] pre-activation, v / pe: [B, dim, h, w]; CUDA tensors, fp32 or 16-bit."""
     if not qk.is_cuda:
         raise RuntimeError("recnext_b200.linattn_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
-    if qk.dtype not in (torch.bfloat16, torch.float16):
-        raise TypeError(f"linattn_forward: 16-bit activations (bfloat16 / float16) only, got {qk.dtype}")
+    if qk.dtype not in _DTYPES:
+        raise TypeError(f"linattn_forward: float32 / bfloat16 / float16 only, got {qk.dtype}")
     qk, v = qk.contiguous(), v.to(qk.dtype).contiguous()
     pe = None if pe is None else pe.to(qk.dtype).contiguous()
     B, dim, H, W = v.shape
@@ -160,12 +160,12 @@ def linattn_forward(qk: torch.Tensor, v: torch.Tensor, pe: Optional[torch.Tensor
     return out
 
 
-LINATTN_HEAD_DIMS = (16, 20, 24, 28, 32, 40)
+LINATTN_HEAD_DIMS = (4, 8, 16, 20, 24, 28, 32, 40)   # 20..40: the RecNeXt-A models; 4, 8, 16: small test models
 
 
 def _linattn_eligible(mod: nn.Module, x: torch.Tensor) -> bool:
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
-    return (not mod.training and x.is_cuda and dt in (torch.bfloat16, torch.float16) and mod.head_dim in LINATTN_HEAD_DIMS
+    return (not mod.training and x.is_cuda and dt in _DTYPES and mod.head_dim in LINATTN_HEAD_DIMS
             and os.environ.get("RECNEXT_LINATTN", "1") != "0" and not torch.jit.is_tracing())
 
 

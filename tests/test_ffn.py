@@ -100,7 +100,7 @@ def test_block_with_fused_ffn_matches_library_path(monkeypatch):
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(4, 64, 56, 56), (3, 128, 28, 28), (3, 256, 14, 14), (2, 40, 56, 56), (2, 6, 9, 13), (1, 3, 25, 42), (2, 4, 7, 7)],
                          ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
 def test_dwdown_kernel_vs_torch(shape, dtype):
     """Downsample token mixer (depthwise 7x7 stride 2, multiplier 2, + bias; reference model/recnext.py:137-138) vs F.conv2d"""
     from recnext_b200.model import dwdown_forward
@@ -111,9 +111,14 @@ def test_dwdown_kernel_vs_torch(shape, dtype):
     w = torch.randn(2 * C, 1, 7, 7, device="cuda") / 7.0
     b = 0.1 * torch.randn(2 * C, device="cuda")
     out = dwdown_forward(x, w, b)
-    ref = F.conv2d(x.float(), w, b, stride=2, padding=3, groups=C)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=3, groups=C)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
     assert out.shape == ref.shape
-    assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < (TOL_BF16 if dtype == torch.bfloat16 else 4e-3)
+    assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < {torch.float32: 1e-5, torch.bfloat16: TOL_BF16, torch.float16: 4e-3}[dtype]
 
 
 @pytest.mark.gpu

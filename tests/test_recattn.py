@@ -140,12 +140,7 @@ def test_cuda_linear_attention_kernel_against_reference(path):
 
     la = m.down[1]
     low = torch.from_numpy(z["low"]).cuda()
-    if la.head_dim not in LINATTN_HEAD_DIMS:   # (toy fixture: head_dim 4) the module keeps the reference's op chain, the kernel refuses
-        with pytest.raises(RuntimeError, match="head_dim"):
-            linattn_forward(la.qk(low).bfloat16(), low.bfloat16(), None, la.num_heads)
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            assert rel_err(la(low).float().cpu().numpy(), z["z"]) < TOL_BF16
-        return
+    assert la.head_dim in LINATTN_HEAD_DIMS
     with torch.no_grad():
         qk_pre = la.qk(low)
         pe = la.pe(low)
@@ -159,7 +154,7 @@ def test_cuda_linear_attention_kernel_against_reference(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("d,heads,n", [(16, 2, 5), (20, 2, 784), (24, 4, 196), (28, 8, 49), (32, 16, 16), (40, 2, 130)])
+@pytest.mark.parametrize("d,heads,n", [(4, 3, 9), (8, 2, 70), (16, 2, 5), (20, 2, 784), (24, 4, 196), (28, 8, 49), (32, 16, 16), (40, 2, 130)])
 def test_cuda_linear_attention_head_dims(d, heads, n):
     """every head_dim of the A-series (model/recattn.py:380-426) against the reference formula in fp32"""
     from recnext_b200.recattn import linattn_forward
@@ -177,3 +172,30 @@ def test_cuda_linear_attention_head_dims(d, heads, n):
     kvm = (k * s) @ (vv.transpose(-1, -2) * s)
     ref = (q_t @ kvm / (q_t @ k.mean(dim=-1, keepdim=True) + 1e-6)).transpose(-1, -2).reshape(B, dim, 1, n) + pe.float()
     assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
+def test_cuda_linear_attention_fp32_parity(path):
+    """fp32 bar of the north star (1e-5) for the linear-attention kernel: fixture inputs/outputs of the unmodified reference"""
+    from recnext_b200.recattn import linattn_forward
+    from tests.helpers import TOL_FP32
+
+    z, meta, sd = _load(path)
+    m = _module(meta, sd)
+    la = m.down[1]
+    low = torch.from_numpy(z["low"])
+    with torch.no_grad():
+        qk_pre, pe = la.qk(low), la.pe(low)          # the two ConvNorms on the CPU in fp32 (reference arithmetic)
+    out = linattn_forward(qk_pre.cuda(), low.cuda(), pe.cuda(), la.num_heads)
+    assert out.dtype == torch.float32
+    assert rel_err(out.cpu().numpy(), z["z"]) < TOL_FP32
+
+
+@pytest.mark.gpu
+def test_cuda_linear_attention_unsupported_head_dim_is_an_error():
+    from recnext_b200.recattn import linattn_forward
+
+    qk = torch.randn(1, 2 * 12, 4, 4, device="cuda").bfloat16()
+    with pytest.raises(RuntimeError, match="head_dim"):
+        linattn_forward(qk, torch.randn(1, 12, 4, 4, device="cuda").bfloat16(), None, 1)   # head_dim 12
