@@ -364,12 +364,34 @@ def main():
                   % (("", "RecAttn2d down / up-add-conv", dom["n"]) if "_a" in MODEL else ("_static", "RecConv", dom["n"])),
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
         "peak_source": peak_src, "bytes_per_launch": dom["bytes"] / max(dom["n"], 1), "avg_launch_ms": dom["ms"] / max(dom["n"], 1),
-        "share_of_step": round(dom["ms"] / ms_total, 4), "all_recconv_share_of_step": round(kern_all_ms / ms_total, 4),
+        "share_of_step": round(dom["ms"] / ms_total, 4), "all_custom_kernels_share_of_step": round(kern_all_ms / ms_total, 4),
         "per_shape": per_shape,
         "note": "algorithmic bytes 2*N*e per launch (SURVEY 8d), CUDA events on the launching stream around every launch of the "
                 "timed steps.  The block is not HBM bound on B200: ~48 MAC per 4 bytes of bf16 traffic; the stencils run on the "
                 "tensor cores as banded-Toeplitz MMAs, bound by shared-memory bandwidth and issue slots (DESIGN.md 3.2)",
     }
+
+    # second roofline: the fused channel-mixer kernel (by time the largest kernel of the step since RecConv got fast).  It is a
+    # pair of GEMMs, so it is reported against the tensor peak too: flops = 2 GEMMs x 2 x C x hidden per pixel.
+    ffn = [r for r in launches if isinstance(r["shape"][0], str) and r["shape"][0] == "ffn"]
+    roofline_ffn = None
+    if ffn:
+        hid_ratio = 2.0 if "_a" not in MODEL else 1.875
+        fl = sum(4.0 * r["shape"][2] * (r["shape"][2] * hid_ratio) * r["shape"][1] * r["shape"][3] * r["shape"][4] for r in ffn)
+        fms = sum(r["ms"] for r in ffn)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                tpeak, tsrc = float(json.load(fh)["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+        except Exception:
+            tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md)"
+        tf = fl / (fms * 1e-3) * 1e-12
+        gbs = sum(r["bytes"] for r in ffn) / (fms * 1e-3) * 1e-9
+        roofline_ffn = {"bound": "tensor", "kernel": "recnext::recnext_ffn_kernel / recnext_ffn_staged_kernel<bf16> (fused channel mixer; %d launches)" % len(ffn),
+                        "achieved": round(tf, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(tf / tpeak, 4), "peak_source": tsrc,
+                        "hbm_gbs_of_3Ne": round(gbs, 1), "hbm_frac": round(gbs / peak, 4), "avg_launch_ms": fms / len(ffn),
+                        "share_of_step": round(fms / ms_total, 4),
+                        "note": "HMMA (mma.sync) kernel: bound by shared-memory operand traffic and pipeline fill at the wide stages, by the GELU's "
+                                "FP32 work at the narrow ones (DESIGN.md 3.3); listed because it is the largest kernel of the step by time"}
 
     if rank != 0:
         D.finalize()
@@ -389,6 +411,8 @@ def main():
         "gpu_launches": n_launch,
         "roofline": roofline,
     }
+    if roofline_ffn is not None:
+        out["roofline_channel_mixer"] = roofline_ffn
     if not args.no_micro and "_a" not in MODEL:
         out["recconv_fwd_bwd"] = recconv_microbench(torch, R, peak)
     if not args.no_cpu_baseline:
