@@ -131,3 +131,25 @@ def test_a_series_full_model_logits_gpu():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         y2 = net(x).float().cpu().numpy()
     assert rel_err(y2, ZA["recnext_a0_224_logits"]) < 5e-2
+
+
+@pytest.mark.gpu
+def test_pipelined_inference_matches_plain_calls():
+    """recnext_b200.infer.PipelinedInference (what bench.py times as e2e): same logits as calling the model batch by batch"""
+    from recnext_b200.infer import PipelinedInference
+    from recnext_b200.model import create_model, replace_batchnorm
+
+    torch.manual_seed(0)
+    net = create_model("recnext_m0").eval()
+    fill_state_dict_(net, seed=0)
+    replace_batchnorm(net)
+    net.cuda()
+    batches = [torch.randn(4, 3, 224, 224).bfloat16().pin_memory() for _ in range(5)]
+    ref = []
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for b in batches:
+            ref.append(net(b.cuda()).float().cpu())
+    got = [y.float().clone() for y in PipelinedInference(net, torch.bfloat16).run(batches)]
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
