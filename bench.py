@@ -109,6 +109,11 @@ def cpu_reference_rate(steps: int, warmup: int, batch: int):
     """images/sec of the reference CPU path on `batch` images per step, all host threads."""
     import torch
 
+    # all the host threads the box has: torchrun exports OMP_NUM_THREADS=1, which would make the reference arm look 8x slower
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     net = build_cpu_reference_model()
     x = torch.randn(batch, 3, RES, RES)
     ts = []
