@@ -428,9 +428,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "model": MODEL, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "resolution": RES,
+        "config": {"workload": WORKLOAD, "variant": MODEL, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "resolution": RES,
                    "parallelism": f"replicas x{world} (no data-path collective)", "weights": "random-init",
-                   "memory_format": args.memory_format + " around RecConv2d (cuDNN 1x1 convs); RecConv2d itself on NCHW planes",
+                   "memory_format": args.memory_format + " (NCHW planes for every kernel of this repo; the stem and stage 3 mixers are library convs)",
                    "l2": "per-step activations (>= 100 MB per stage-0 tensor) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": x_host.numel() * 2,
