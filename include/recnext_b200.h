@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RECNEXT_ABI_VERSION 1
+#define RECNEXT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RECNEXT_API __attribute__((visibility("default")))
@@ -76,8 +76,17 @@ typedef struct recconv_params {
 RECNEXT_API int recnext_abi_version(void);
 RECNEXT_API const char* recnext_last_error(void);
 
-/* y = RecConv2d(x).  No workspace needed. */
+/*
+ * y = RecConv2d(x).  Planes whose whole pyramid fits in one SM's shared memory (every RecNeXt stage shape at 224 px,
+ * detection stages 2-3, 16-bit detection stages 0-1) run fused and need no workspace.  Larger planes (fp32 detection
+ * stages 0-1) are STREAMED level by level through an fp32 workspace of recconv_forward_workspace_bytes(d) bytes
+ * (0 when the fused kernels take the call); recconv_forward == recconv_forward_ws without a workspace and returns
+ * RECNEXT_EWORKSPACE for those.
+ */
 RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream);
+RECNEXT_API size_t recconv_forward_workspace_bytes(const recconv_desc* d);
+RECNEXT_API int recconv_forward_ws(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* workspace,
+                                   size_t workspace_bytes, void* stream);
 
 /*
  * Backward.  gx: [B,C,H,W] in d->dtype.  Weight grads are fp32 and PACKED:
@@ -85,7 +94,9 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
  *                            model/recnext.py:21,28), slot 1+j = convs.{j}.weight
  *   gb [(level+2), C] or NULL (same slot order); must be non-NULL iff has_bias.
  * Both are overwritten (not accumulated).  The result is deterministic (fixed reduction order).
- * workspace: recconv_backward_workspace_bytes(d) bytes of device memory, 16-byte aligned.
+ * workspace: recconv_backward_workspace_bytes(d) bytes of device memory, 16-byte aligned: a few hundred KB of partial
+ * sums for the fused kernels; planes whose pyramid does not fit on chip (detection stages 0-1) take the streamed path,
+ * whose workspace holds the fp32 pyramid and its gradients (~14 bytes per element of x).
  */
 RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d);
 RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p, const void* x, const void* gy, void* gx,

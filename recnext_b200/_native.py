@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_lib", "librecnext_b200.so")
 MAX_LEVEL = 6
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, BF16, F16 = 0, 1, 2
 BILINEAR, NEAREST = 0, 1
@@ -54,6 +54,11 @@ def lib() -> ctypes.CDLL:
     L.recconv_forward.restype = ctypes.c_int
     L.recconv_forward.argtypes = [ctypes.POINTER(RecConvDesc), ctypes.POINTER(RecConvParams), ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_void_p]
+    L.recconv_forward_workspace_bytes.restype = ctypes.c_size_t
+    L.recconv_forward_workspace_bytes.argtypes = [ctypes.POINTER(RecConvDesc)]
+    L.recconv_forward_ws.restype = ctypes.c_int
+    L.recconv_forward_ws.argtypes = [ctypes.POINTER(RecConvDesc), ctypes.POINTER(RecConvParams), ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.recconv_backward_workspace_bytes.restype = ctypes.c_size_t
     L.recconv_backward_workspace_bytes.argtypes = [ctypes.POINTER(RecConvDesc)]
     L.recconv_backward.restype = ctypes.c_int
@@ -87,6 +92,7 @@ def check(rc: int, what: str) -> None:
 
 
 EXPORTS = [
-    "recnext_abi_version", "recnext_last_error", "recconv_forward", "recconv_backward_workspace_bytes", "recconv_backward",
+    "recnext_abi_version", "recnext_last_error", "recconv_forward", "recconv_forward_workspace_bytes", "recconv_forward_ws",
+    "recconv_backward_workspace_bytes", "recconv_backward",
     "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward", "recnext_ffn_forward", "recnext_dwdown_forward", "recnext_linattn_forward",
 ]

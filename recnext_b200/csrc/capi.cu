@@ -10,6 +10,8 @@
 #include "recconv_body.cuh"
 #include "wplan.h"
 #include "mplan.h"
+#include "gstream.h"
+#include "devcfg.h"
 #include <stdlib.h>
 
 namespace recnext {
@@ -112,16 +114,17 @@ static long long* prof_buffer() {
     return g_prof;
 }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
 static int device_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-            sms = v;
-        else
-            return 148;  // B200; used only for planning when no device is visible (plan_describe on a CPU box)
+    static int sms[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;  // planning without a visible device (plan_describe on a CPU box)
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms[dev] = v;
+        else return 148;
     }
-    return sms;
+    return sms[dev];
 }
 
 static int check_desc(const recconv_desc* d) {
@@ -135,15 +138,25 @@ static int check_desc(const recconv_desc* d) {
     return 0;
 }
 
+// 0: big-plane plan made; 1: the plane's pyramid does not fit in shared memory (caller takes the streamed path); < 0: error
 static int make_plan(const recconv_desc* d, bool bwd, Plan& pl) {
     PlanOptions opt;
     opt.num_sms = device_sms();
     const int rc = rc_make_plan(pl, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, bwd ? 1 : 0, opt);
-    if (rc == 1)
-        return fail(RECNEXT_EUNSUPPORTED, "recconv: a %dx%d plane pyramid (level %d, %s) does not fit in 227 KB of shared memory",
-                    d->H, d->W, d->level, bwd ? "backward" : "forward");
+    if (rc == 1) return 1;
     if (rc) return fail(RECNEXT_EINVAL, "recconv: bad arguments");
     return 0;
+}
+static GStreamDesc stream_desc(const recconv_desc* d) {
+    GStreamDesc g;
+    g.B = d->B; g.C = d->C; g.H = d->H; g.W = d->W; g.K = d->k; g.L = d->level; g.mode = d->mode; g.dtype = d->dtype; g.wdtype = d->wdtype;
+    g.has_bias = d->has_bias; g.num_sms = device_sms();
+    return g;
+}
+// RECNEXT_PATH=stream forces the streamed path (tests, A/B measurements)
+static bool stream_forced() {   // read on every call so that one process can test both paths
+    const char* e = getenv("RECNEXT_PATH");
+    return e && strcmp(e, "stream") == 0;
 }
 
 // 0: team-resident plan made; 1: not eligible (use the big-plane path)
@@ -232,7 +245,25 @@ extern "C" {
 RECNEXT_API int recnext_abi_version(void) { return RECNEXT_ABI_VERSION; }
 RECNEXT_API const char* recnext_last_error(void) { return g_err; }
 
-RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream) {
+// 0: one of the on-chip kernels takes this forward; 1: streamed path (needs a workspace)
+static int forward_needs_stream(const recconv_desc* d) {
+    if (stream_forced()) return 1;
+    MPlan mp;
+    if (make_mplan(d, mp) == 0) return 0;
+    WPlan wp;
+    if (make_wplan(d, false, wp) == 0) return 0;
+    Plan pl;
+    return make_plan(d, false, pl) == 1 ? 1 : 0;
+}
+
+RECNEXT_API size_t recconv_forward_workspace_bytes(const recconv_desc* d) {
+    if (check_desc(d)) return 0;
+    if (d->B == 0 || d->C == 0) return 0;
+    return forward_needs_stream(d) ? gstream_workspace_bytes(stream_desc(d), false) : 0;
+}
+
+RECNEXT_API int recconv_forward_ws(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
     if (int rc = check_desc(d)) return rc;
     if (d->B == 0 || d->C == 0) return RECNEXT_OK;
     if (!x || !y) return fail(RECNEXT_EINVAL, "recconv_forward: null tensor");
@@ -240,14 +271,14 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
     if (int rc = fill_args(d, p, a)) return rc;
     a.x = x; a.out = y;
     MPlan mp;
-    if ((((uintptr_t)x | (uintptr_t)y) & 3) == 0 && make_mplan(d, mp) == 0) {
+    if (!stream_forced() && (((uintptr_t)x | (uintptr_t)y) & 3) == 0 && make_mplan(d, mp) == 0) {
         if (((uintptr_t)x & 15) != 0) mp.use_tma = 0;  // bulk copies need 16-byte aligned sources (raw buffer stays allocated)
         const cudaError_t e = m_launch(mp, a, (cudaStream_t)stream);
         if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward(mma): %s", cudaGetErrorString(e));
         return RECNEXT_OK;
     }
     WPlan wp;
-    if (make_wplan(d, false, wp) == 0) {
+    if (!stream_forced() && make_wplan(d, false, wp) == 0) {
         a.prof = prof_buffer();
         if (((uintptr_t)x & 15) != 0) wp.use_tma = 0;  // bulk copies need 16-byte aligned sources
         const cudaError_t e = w_pick(d->k, d->dtype, false)(wp, a, (cudaStream_t)stream);
@@ -255,11 +286,26 @@ RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, 
         return RECNEXT_OK;
     }
     Plan pl;
-    if (int rc = make_plan(d, false, pl)) return rc;
+    const int prc = stream_forced() ? 1 : make_plan(d, false, pl);
+    if (prc < 0) return prc;
+    if (prc == 1) {  // the pyramid of one plane does not fit on chip: level-by-level through the workspace (gstream.cu)
+        const GStreamDesc g = stream_desc(d);
+        const size_t need = gstream_workspace_bytes(g, false);
+        if (!workspace || workspace_bytes < need)
+            return fail(RECNEXT_EWORKSPACE, "recconv_forward: a %dx%d plane pyramid (level %d) does not fit in shared memory; the streamed path needs a "
+                        "workspace of %zu bytes (recconv_forward_workspace_bytes), got %zu", d->H, d->W, d->level, need, workspace_bytes);
+        const cudaError_t e = gstream_launch(g, a, workspace, false, nullptr, nullptr, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward(stream): %s", cudaGetErrorString(e));
+        return RECNEXT_OK;
+    }
     rc_launch_fn fn = pick(d->k, d->dtype, false);
     const cudaError_t e = fn(pl, a, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_forward: %s", cudaGetErrorString(e));
     return RECNEXT_OK;
+}
+
+RECNEXT_API int recconv_forward(const recconv_desc* d, const recconv_params* p, const void* x, void* y, void* stream) {
+    return recconv_forward_ws(d, p, x, y, nullptr, 0, stream);
 }
 
 // RecAttn2d pieces: variants 1 / 2 of the tensor-core forward kernel
@@ -344,9 +390,11 @@ RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
     if (check_desc(d)) return 0;
     if (d->B == 0 || d->C == 0) return 0;
     WPlan wp;
-    if (make_wplan(d, true, wp) == 0) return (size_t)wp.ws_partial_floats * sizeof(float);
+    if (!stream_forced() && make_wplan(d, true, wp) == 0) return (size_t)wp.ws_partial_floats * sizeof(float);
     Plan pl;
-    if (make_plan(d, true, pl)) return 0;
+    const int prc = stream_forced() ? 1 : make_plan(d, true, pl);
+    if (prc == 1) return gstream_workspace_bytes(stream_desc(d), true);
+    if (prc) return 0;
     return (size_t)pl.ws_partial_floats * sizeof(float);
 }
 
@@ -371,7 +419,7 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
     Plan pl;
     int n_partials = 0, wstride = 0;
     cudaError_t e;
-    if (make_wplan(d, true, wp) == 0) {
+    if (!stream_forced() && make_wplan(d, true, wp) == 0) {
         const size_t need = (size_t)wp.ws_partial_floats * sizeof(float);
         if (!workspace || workspace_bytes < need)
             return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
@@ -380,7 +428,17 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
         e = w_pick(d->k, d->dtype, true)(wp, a, (cudaStream_t)stream);
         n_partials = wp.tpc; wstride = wp.wstride;
     } else {
-        if (int rc = make_plan(d, true, pl)) return rc;
+        const int prc = stream_forced() ? 1 : make_plan(d, true, pl);
+        if (prc < 0) return prc;
+        if (prc == 1) {  // the plane's pyramid does not fit on chip: streamed backward (gstream.cu), writes gw / gb itself
+            const GStreamDesc g = stream_desc(d);
+            const size_t need = gstream_workspace_bytes(g, true);
+            if (!workspace || workspace_bytes < need)
+                return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
+            e = gstream_launch(g, a, workspace, true, gw, gb, (cudaStream_t)stream);
+            if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward(stream): %s", cudaGetErrorString(e));
+            return RECNEXT_OK;
+        }
         const size_t need = (size_t)pl.ws_partial_floats * sizeof(float);
         if (!workspace || workspace_bytes < need)
             return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
@@ -408,7 +466,7 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
     if (int rc = check_desc(d)) return rc;
     if (!buf || !buflen) return fail(RECNEXT_EINVAL, "recconv_plan_describe: null buffer");
     MPlan mp;
-    if (!backward && make_mplan(d, mp) == 0) {
+    if (!stream_forced() && !backward && make_mplan(d, mp) == 0) {
         snprintf(buf, buflen,
                  "fwd tensor-core k=5 L=%d [%d,%d,%d,%d] planes/batch=%d warps/team=%d teams/CTA=%d threads=%d grid=%d smem=%d B team=%d B "
                  "plane=%d B frag-regs/channel=%d tma=%d geometry=%s",
@@ -417,7 +475,7 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
         return RECNEXT_OK;
     }
     WPlan wp;
-    if (make_wplan(d, backward != 0, wp) == 0) {
+    if (!stream_forced() && make_wplan(d, backward != 0, wp) == 0) {
         snprintf(buf, buflen,
                  "%s team-resident k=%d L=%d [%d,%d,%d,%d] planes/batch=%d warps/team=%d teams/CTA=%d threads=%d grid=%d lanes/plane=%d "
                  "teams/channel-group=%d smem=%d B team=%d B plane=%d B tma=%d",
@@ -426,7 +484,13 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
         return RECNEXT_OK;
     }
     Plan pl;
-    if (int rc = make_plan(d, backward != 0, pl)) return rc;
+    const int prc = stream_forced() ? 1 : make_plan(d, backward != 0, pl);
+    if (prc < 0) return prc;
+    if (prc == 1) {
+        snprintf(buf, buflen, "%s streamed k=%d L=%d [%d,%d,%d,%d] level-by-level through a %zu-byte fp32 workspace (plane pyramid exceeds shared memory)",
+                 backward ? "bwd" : "fwd", d->k, d->level, d->B, d->C, d->H, d->W, gstream_workspace_bytes(stream_desc(d), backward != 0));
+        return RECNEXT_OK;
+    }
     int n = snprintf(buf, buflen,
                      "%s k=%d L=%d [%d,%d,%d,%d] planes/CTA=%d lanes/plane=%d units=%d threads=%d grid=%dx%d (cg x chunk, %d img/chunk) "
                      "smem=%d B plane=%d B tma=%d share_raw=%d rpi=",

@@ -7,6 +7,7 @@
 // fp32 (zero border), each thread produces a 2 x 2 block of BOTH output channels from one 9 x 9 register window (81 shared
 // loads for 392 FMAs), the filters come from shared memory as broadcasts.  Memory bound by design: x read once, out written once.
 #include <cuda_runtime.h>
+#include "devcfg.h"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -98,14 +99,14 @@ int dwdown_launch(int B, int C, int H, int W, int dtype, const void* x, const fl
     while (PP > 1 && PP * pbytes > 72 * 1024) --PP;      // keep three CTAs per SM
     const long nplanes = (long)B * C;
     const size_t smem = PP * pbytes;
-    static int configured = 0;
-    if (!configured) {
-        *err = cudaFuncSetAttribute(recnext_dwdown_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (*err == cudaSuccess) *err = cudaFuncSetAttribute(recnext_dwdown_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (*err == cudaSuccess) *err = cudaFuncSetAttribute(recnext_dwdown_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (*err != cudaSuccess) return 2;
-        configured = 1;
-    }
+    static DeviceOnce configured = {};
+    *err = rc_once_per_device(configured, [] {
+        cudaError_t e = cudaFuncSetAttribute(recnext_dwdown_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_dwdown_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_dwdown_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        return e;
+    });
+    if (*err != cudaSuccess) return 2;
     const int grid = (int)((nplanes + PP - 1) / PP);
     if (dtype == 0) recnext_dwdown_kernel<float><<<grid, 256, smem, stream>>>((const float*)x, w, b, (float*)out, C, H, W, Ho, Wo, pitch, PP, nplanes);
     else if (dtype == 1) recnext_dwdown_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)x, w, b, (__nv_bfloat16*)out, C, H, W, Ho, Wo, pitch, PP, nplanes);

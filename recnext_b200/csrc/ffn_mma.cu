@@ -19,6 +19,7 @@
 // Warp-level mma.sync (HMMA), not tcgen05: K = C is 64..256 and the pixel tile is tiny, the kernel is bound by HBM and
 // by the GELU's FP32 work, not by tensor throughput; a tcgen05/TMEM version is the next step for the wide stages.
 #include <cuda_runtime.h>
+#include "devcfg.h"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -420,26 +421,28 @@ int ffn_make_plan(FfnPlan& pl, int B, int C, int HID, int HW, int dtype) {
 
 cudaError_t ffn_launch(const FfnPlan& pl, const void* y, const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
                        cudaStream_t stream) {
-    static int configured = 0;  // benign race: idempotent
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(recnext_ffn_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = 1;
+    static DeviceOnce configured = {};
+    {
+        const cudaError_t e0 = rc_once_per_device(configured, [] {
+            cudaError_t e = cudaFuncSetAttribute(recnext_ffn_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return e;
+        });
+        if (e0 != cudaSuccess) return e0;
     }
     const int grid = pl.B * pl.tiles;
     if (pl.staged) {
-        static int configured_s = 0;
-        if (!configured_s) {
+        static DeviceOnce configured_s = {};
+        const cudaError_t e1 = rc_once_per_device(configured_s, [] {
             cudaError_t e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__nv_bfloat16, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__nv_bfloat16, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__half, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(recnext_ffn_staged_kernel<__half, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) return e;
-            configured_s = 1;
-        }
+            return e;
+        });
+        if (e1 != cudaSuccess) return e1;
         const bool k64 = pl.kc == 64;
 #define FFN_LAUNCH_S(TT, KC) recnext_ffn_staged_kernel<TT, KC, KC><<<grid, 512, pl.smem_bytes, stream>>>(pl, (const TT*)y, (const TT*)x, (const TT*)w1, b1, (const TT*)w2, b2, (TT*)out)
         if (pl.dtype == 1) { if (k64) FFN_LAUNCH_S(__nv_bfloat16, 64); else FFN_LAUNCH_S(__nv_bfloat16, 32); }

@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include "recconv_device.cuh"  // mbarrier / cp.async.bulk wrappers, KernelArgs, IdxLam tables
 #include "mplan.h"
+#include "devcfg.h"
 #include <string.h>
 #include <type_traits>
 
@@ -798,12 +799,11 @@ inline bool m_try_static(const MPlan& pl, const KernelArgs& a, cudaStream_t stre
     if (pl.variant != 0 || pl.H != H0 || pl.W != W0 || pl.L != L0 || pl.G != G0) return false;
     const MPlan st = m_static_patched(sp, pl);
     if (memcmp(&st, &pl, sizeof(MPlan)) != 0) return false;
-    static int configured = 0;  // benign race: idempotent
-    if (!configured) {
-        err = cudaFuncSetAttribute(recconv_mfwd_static_kernel<T, H0, W0, L0, G0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err != cudaSuccess) return true;
-        configured = 1;
-    }
+    static DeviceOnce configured = {};
+    err = rc_once_per_device(configured, [] {
+        return cudaFuncSetAttribute(recconv_mfwd_static_kernel<T, H0, W0, L0, G0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (err != cudaSuccess) return true;
     recconv_mfwd_static_kernel<T, H0, W0, L0, G0><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
     err = cudaGetLastError();
     return true;
@@ -832,12 +832,9 @@ inline cudaError_t m_launch_fwd_t(const MPlan& pl, const KernelArgs& a, cudaStre
         if (m_try_static<T, 14, 14, 2, 4>(pl, a, stream, err)) return err;
         if (m_try_static<T, 7, 7, 1, 8>(pl, a, stream, err)) return err;
     }
-    static int configured = 0;  // benign race: idempotent
-    if (!configured) {
-        err = cudaFuncSetAttribute(recconv_mfwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (err != cudaSuccess) return err;
-        configured = 1;
-    }
+    static DeviceOnce configured = {};
+    err = rc_once_per_device(configured, [] { return cudaFuncSetAttribute(recconv_mfwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    if (err != cudaSuccess) return err;
     if (pl.threads > 512) return cudaErrorInvalidConfiguration;  // planned for a specialised kernel that did not match
     recconv_mfwd_kernel<T><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
     return cudaGetLastError();

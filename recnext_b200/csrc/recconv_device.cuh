@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "recconv_body.cuh"
+#include "devcfg.h"
 
 namespace recnext {
 
@@ -204,12 +205,9 @@ typedef cudaError_t (*rc_launch_fn)(const Plan&, const KernelArgs&, cudaStream_t
 
 template <int K, typename T, bool BWD>
 cudaError_t rc_launch(const Plan& pl, const KernelArgs& a, cudaStream_t stream) {
-    static int configured_smem = 0;  // largest opt-in set so far (benign race: idempotent)
-    if (pl.smem_bytes > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(recconv_kernel<K, T, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        configured_smem = 227 * 1024;
-    }
+    static DeviceOnce configured = {};
+    const cudaError_t e0 = rc_once_per_device(configured, [] { return cudaFuncSetAttribute(recconv_kernel<K, T, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    if (e0 != cudaSuccess) return e0;
     recconv_kernel<K, T, BWD><<<pl.n_cg * pl.n_chunk, pl.T, pl.smem_bytes, stream>>>(pl, a);
     return cudaGetLastError();
 }

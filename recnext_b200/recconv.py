@@ -87,12 +87,15 @@ def recconv_forward(x: torch.Tensor, weights: List[torch.Tensor], biases: Option
     wd, ws, bs = _prep_params(x, weights, biases)
     d = _desc(x, k, level, mode, wd, bs is not None)
     y = torch.empty_like(x)
+    # 0 for every plane whose pyramid fits on chip (the fused kernels); planes that do not fit are streamed through a workspace
+    nbytes = N.lib().recconv_forward_workspace_bytes(ctypes.byref(d))
+    ws_buf = torch.empty((nbytes,), dtype=torch.uint8, device=x.device) if nbytes else None
     with torch.cuda.device(x.device):
         if _timing is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        N.check(N.lib().recconv_forward(ctypes.byref(d), ctypes.byref(_params(ws, bs)), x.data_ptr(), y.data_ptr(), _stream(x)),
-                "recconv_forward")
+        N.check(N.lib().recconv_forward_ws(ctypes.byref(d), ctypes.byref(_params(ws, bs)), x.data_ptr(), y.data_ptr(),
+                                           ws_buf.data_ptr() if nbytes else None, nbytes, _stream(x)), "recconv_forward")
         if _timing is not None:
             ev1.record()
             _timing.append((ev0, ev1, 2 * x.numel() * x.element_size(), tuple(x.shape)))

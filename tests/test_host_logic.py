@@ -59,8 +59,11 @@ def test_bad_arguments_are_errors(native):
     assert b"kernel_size" in L.recnext_last_error()
     d = native.RecConvDesc(1, 4, 8, 8, 5, 9, 0, 0, 0, 0)  # level too deep
     assert L.recconv_plan_describe(ctypes.byref(d), 0, buf, 256) == -1
-    d = native.RecConvDesc(2, 64, 200, 336, 5, 4, 0, 1, 0, 0)  # detection stage 0: does not fit on chip (yet)
-    assert L.recconv_plan_describe(ctypes.byref(d), 1, buf, 256) == -2
+    d = native.RecConvDesc(2, 64, 200, 336, 5, 4, 0, 1, 0, 0)  # detection stage 0: pyramid exceeds shared memory -> streamed path
+    assert L.recconv_plan_describe(ctypes.byref(d), 1, buf, 256) == 0 and b"streamed" in buf.value
+    assert L.recconv_backward_workspace_bytes(ctypes.byref(d)) > 2 * 64 * 200 * 336 * 4
+    d = native.RecConvDesc(256, 64, 56, 56, 5, 4, 0, 1, 0, 0)  # the fused kernels need no forward workspace
+    assert L.recconv_forward_workspace_bytes(ctypes.byref(d)) == 0
 
 
 def test_plan_describe_baseline_shapes(native):

@@ -98,14 +98,67 @@ def test_384px_stage0_forward():
     assert rel_err(y.cpu().numpy(), O.forward(x, p, "bilinear")) < TOL_FP32
 
 
-def test_fixture_big_plane_forward():
+def test_fixture_big_plane_forward_backward():
+    """Detection stage 1, unpadded odd width (100x167, level 3): outputs and every gradient of the unmodified reference.
+    The fp32 backward pyramid does not fit on chip: the streamed path (csrc/gstream.cu) takes it."""
     g = load_recconv_golden(os.path.join(GOLDEN, "recconv_det_odd_100x167_L3.npz"))
-    R = _R()
-    ws, bs = _lists(g["params"])
-    y = R.recconv_forward(torch.from_numpy(g["z"]["x"]).to(DEV), ws, bs, 5, 3, "bilinear")
-    assert rel_err(y.cpu().numpy(), g["z"]["y"]) < TOL_FP32
-    with pytest.raises(RuntimeError, match="does not fit"):
-        R.recconv_backward(torch.from_numpy(g["z"]["x"]).to(DEV), torch.from_numpy(g["z"]["gy"]).to(DEV), ws, bs, 5, 3, "bilinear")
+    z, p = g["z"], g["params"]
+    y, gx, gw, gb = _run(z["x"], z["gy"], p, g["mode"], torch.float32)
+    ref = dict(gx=z["gx"], down_w=z["g:down.weight"], convs_w=[z[f"g:convs.{j}.weight"] for j in range(g["L"] + 1)])
+    _compare(y, gx, gw, gb, z["y"], ref, p, TOL_FP32)
+    y, gx, gw, gb = _run(z["x"], z["gy"], p, g["mode"], torch.bfloat16)
+    _compare(y, gx, gw, gb, z["y"], ref, p, TOL_BF16)
+
+
+@pytest.fixture
+def streamed_path():
+    """Forces the level-by-level streamed kernels (the path of planes whose pyramid does not fit on chip)."""
+    old = os.environ.get("RECNEXT_PATH")
+    os.environ["RECNEXT_PATH"] = "stream"
+    yield
+    if old is None:
+        del os.environ["RECNEXT_PATH"]
+    else:
+        os.environ["RECNEXT_PATH"] = old
+
+
+@pytest.mark.parametrize("path", recconv_golden_files(), ids=lambda p: os.path.basename(p)[8:-4])
+def test_streamed_path_fixture_fp32(path, streamed_path):
+    """Every reference fixture (k = 3/5/7, nearest, bias, odd sizes, level 0..4) through the streamed kernels."""
+    g = load_recconv_golden(path)
+    z, p = g["z"], g["params"]
+    assert "streamed" in _R().plan_describe(z["x"].shape, p.k, p.level, g["mode"], torch.float32, g["bias"], True)
+    y, gx, gw, gb = _run(z["x"], z["gy"], p, g["mode"], torch.float32)
+    ref = dict(gx=z["gx"], down_w=z["g:down.weight"], convs_w=[z[f"g:convs.{j}.weight"] for j in range(g["L"] + 1)])
+    if g["bias"]:
+        ref["down_b"] = z["g:down.bias"]
+        ref["convs_b"] = [z[f"g:convs.{j}.bias"] for j in range(g["L"] + 1)]
+    _compare(y, gx, gw, gb, z["y"], ref, p, TOL_FP32)
+
+
+# BASELINE configs[4]: RecNeXt-M3 backbone at detection scale 800x1333 (padded to 800x1344), 2 images per GPU
+_DET_CASES = [
+    (2, 64, 200, 336, 4),    # stage 0
+    (2, 128, 100, 168, 3),   # stage 1
+    (2, 64, 200, 334, 4),    # stage 0, unpadded 1333-px width (odd sizes down the pyramid: 334 -> 167 -> 84 -> 42 -> 21)
+]
+
+
+@pytest.mark.parametrize("case", _DET_CASES, ids=lambda c: "x".join(str(v) for v in c))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_detection_scale_forward_backward(case, dtype):
+    """Forward and ALL gradients at the detection plane sizes against the C oracle (fp64 tap sums)."""
+    B, C, H, W, L = case
+    rng = np.random.default_rng(7)
+    p = O.RecConvParams.random(C, 5, L, False, rng)
+    x = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    gy = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    if dtype == torch.bfloat16:
+        x = torch.from_numpy(x).bfloat16().float().numpy()
+        gy = torch.from_numpy(gy).bfloat16().float().numpy()
+    y, gx, gw, gb = _run(x, gy, p, "bilinear", dtype)
+    tol = TOL_BF16 if dtype == torch.bfloat16 else TOL_FP32
+    _compare(y, gx, gw, gb, O.forward(x, p, "bilinear"), O.backward(x, gy, p, "bilinear"), p, tol)
 
 
 # BASELINE.json per-stage shapes (SURVEY.md §8d) at reduced batch, plus ragged / odd / tiny cases.
