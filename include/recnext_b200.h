@@ -133,6 +133,22 @@ RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_
                                     const void* w1, const float* b1, const void* w2, const float* b2, void* out, void* stream);
 
 /*
+ * The same channel mixer on the 5th-generation tensor cores (tcgen05.mma with TMEM accumulators, weights streamed by TMA
+ * bulk copies; csrc/ffn_tc.cu) — the default path of recnext_b200.model.  It serves every RecNeXt width (C % 8 == 0,
+ * C <= 768, any hidden width, any plane size).  The weights are consumed as a PACKED stream: 128 x 64 tiles in the
+ * kernel's consumption order, each stored as the shared-memory image of a K-major tcgen05 operand, so that a tile is one
+ * contiguous bulk copy.
+ *   recnext_ffn_packed_bytes(C, hidden)          size of the packed stream (0 if the shape is not served)
+ *   recnext_ffn_pack(..., w1, w2, packed)        w1 [hidden, C], w2 [C, hidden] (16-bit, row-major) -> packed (device kernel)
+ *   recnext_ffn_forward_packed(...)              same contract as recnext_ffn_forward with (w1, w2) replaced by `packed`
+ * Returns RECNEXT_EUNSUPPORTED (nothing launched) for other dtypes / widths.
+ */
+RECNEXT_API size_t recnext_ffn_packed_bytes(int32_t C, int32_t hidden);
+RECNEXT_API int recnext_ffn_pack(int32_t C, int32_t hidden, int32_t dtype, const void* w1, const void* w2, void* packed, void* stream);
+RECNEXT_API int recnext_ffn_forward_packed(int32_t B, int32_t C, int32_t hidden, int32_t HW, int32_t dtype, const void* y, const void* x,
+                                           const void* packed, const float* b1, const float* b2, void* out, void* stream);
+
+/*
  * Token mixer of a `Downsample` block: depthwise 7x7 stride-2 conv with channel multiplier 2 and the
  * eval-mode BatchNorm that follows it folded into (w, b) by the caller — replaces
  *     self.norm(self.token_mixer(x))      model/recnext.py:137-138,145

@@ -81,6 +81,12 @@ def lib() -> ctypes.CDLL:
     L.recnext_dwdown_forward.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 5
     L.recnext_ffn_forward.restype = ctypes.c_int
     L.recnext_ffn_forward.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 8
+    L.recnext_ffn_packed_bytes.restype = ctypes.c_size_t
+    L.recnext_ffn_packed_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    L.recnext_ffn_pack.restype = ctypes.c_int
+    L.recnext_ffn_pack.argtypes = [ctypes.c_int32] * 3 + [ctypes.c_void_p] * 4
+    L.recnext_ffn_forward_packed.restype = ctypes.c_int
+    L.recnext_ffn_forward_packed.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 7
     _lib = L
     return L
 
@@ -94,5 +100,5 @@ def check(rc: int, what: str) -> None:
 EXPORTS = [
     "recnext_abi_version", "recnext_last_error", "recconv_forward", "recconv_forward_workspace_bytes", "recconv_forward_ws",
     "recconv_backward_workspace_bytes", "recconv_backward",
-    "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward", "recnext_ffn_forward", "recnext_dwdown_forward", "recnext_linattn_forward",
+    "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward", "recnext_ffn_forward", "recnext_ffn_packed_bytes", "recnext_ffn_pack", "recnext_ffn_forward_packed", "recnext_dwdown_forward", "recnext_linattn_forward",
 ]

@@ -21,7 +21,7 @@ LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "librecnext_b200.so")
 OBJDIR = os.path.join(ROOT, "build", "obj")
 
-SOURCES = ["capi.cu", "recconv_k3.cu", "recconv_k5.cu", "recconv_k7.cu", "recconv_w3.cu", "recconv_w5.cu", "recconv_w7.cu", "recconv_m5.cu", "ffn_mma.cu", "dwdown.cu", "linattn.cu", "gstream.cu"]
+SOURCES = ["capi.cu", "recconv_k3.cu", "recconv_k5.cu", "recconv_k7.cu", "recconv_w3.cu", "recconv_w5.cu", "recconv_w7.cu", "recconv_m5.cu", "ffn_mma.cu", "dwdown.cu", "linattn.cu", "gstream.cu", "ffn_tc.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -89,4 +89,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    try:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    except RuntimeError as ex:
+        print(str(ex)[-6000:])
+        print("BUILD FAILED")
+        sys.exit(1)

@@ -11,6 +11,7 @@
 #include "wplan.h"
 #include "mplan.h"
 #include "gstream.h"
+#include "ffn_tc.h"
 #include "devcfg.h"
 #include <stdlib.h>
 
@@ -108,7 +109,10 @@ static long long* prof_buffer() {
     if (!init) {
         init = 1;
         const char* e = getenv("RECNEXT_PROF");
-        if (e && atoi(e)) { if (cudaMalloc(&g_prof, 4096 * sizeof(long long)) != cudaSuccess) g_prof = nullptr; }
+        if ((e && atoi(e)) || getenv("RECNEXT_FFN_PROF")) {
+            const cudaError_t me = cudaMalloc(&g_prof, 4096 * sizeof(long long));
+            if (me != cudaSuccess) { fprintf(stderr, "recnext: profiling buffer: %s\n", cudaGetErrorString(me)); g_prof = nullptr; }
+        }
     }
     if (g_prof) cudaMemset(g_prof, 0, 4096 * sizeof(long long));
     return g_prof;
@@ -383,6 +387,40 @@ RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_
                     "(2C + hidden) pixel-tile rows in 227 KB of shared memory (got C=%d hidden=%d HW=%d dtype=%d)", C, hidden, HW, dtype);
     const cudaError_t e = ffn_launch(pl, y, x, w1, b1, w2, b2, out, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recnext_ffn_forward: %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
+}
+
+// ---- tcgen05 channel mixer (ffn_tc.cu)
+RECNEXT_API size_t recnext_ffn_packed_bytes(int32_t C, int32_t hidden) {
+    FfnTcPlan pl;
+    if (C < 1 || hidden < 1 || ffn_tc_make_plan(pl, 1, C, hidden, 8, RECNEXT_BF16, device_sms())) return 0;
+    return pl.packed_bytes;
+}
+
+RECNEXT_API int recnext_ffn_pack(int32_t C, int32_t hidden, int32_t dtype, const void* w1, const void* w2, void* packed, void* stream) {
+    if (!w1 || !w2 || !packed) return fail(RECNEXT_EINVAL, "recnext_ffn_pack: null tensor");
+    FfnTcPlan pl;
+    if (C < 1 || hidden < 1 || ffn_tc_make_plan(pl, 1, C, hidden, 8, dtype, device_sms()))
+        return fail(RECNEXT_EUNSUPPORTED, "recnext_ffn_pack: needs 16-bit weights and C %% 8 == 0 (got C=%d hidden=%d dtype=%d)", C, hidden, dtype);
+    const cudaError_t e = ffn_tc_pack(pl, w1, w2, packed, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recnext_ffn_pack: %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
+}
+
+RECNEXT_API int recnext_ffn_forward_packed(int32_t B, int32_t C, int32_t hidden, int32_t HW, int32_t dtype, const void* y, const void* x,
+                                           const void* packed, const float* b1, const float* b2, void* out, void* stream) {
+    if (B < 0 || C < 1 || hidden < 1 || HW < 1) return fail(RECNEXT_EINVAL, "recnext_ffn_forward_packed: bad shape [%d,%d,%d] hidden %d", B, C, HW, hidden);
+    if (B == 0) return RECNEXT_OK;
+    if (!y || !x || !packed || !b1 || !b2 || !out) return fail(RECNEXT_EINVAL, "recnext_ffn_forward_packed: null tensor");
+    if ((((uintptr_t)y | (uintptr_t)x | (uintptr_t)out | (uintptr_t)packed) & 15) != 0)
+        return fail(RECNEXT_EINVAL, "recnext_ffn_forward_packed: tensors must be 16-byte aligned");
+    FfnTcPlan pl;
+    if (ffn_tc_make_plan(pl, B, C, hidden, HW, dtype, device_sms()))
+        return fail(RECNEXT_EUNSUPPORTED, "recnext_ffn_forward_packed: needs 16-bit activations, C %% 8 == 0 and C <= 768 (got C=%d hidden=%d HW=%d dtype=%d)",
+                    C, hidden, HW, dtype);
+    if (getenv("RECNEXT_FFN_PROF")) ffn_tc_set_prof(prof_buffer());   // stamps are read back with recnext_debug_prof()
+    const cudaError_t e = ffn_tc_launch(pl, y, x, packed, b1, b2, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recnext_ffn_forward_packed: %s", cudaGetErrorString(e));
     return RECNEXT_OK;
 }
 

@@ -94,19 +94,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarri
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) expires: a waiting warp issues almost
+// no instructions (a bare spin loop costs the working warps of the same scheduler a quarter of their issue slots, ncu)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
+// A wait that outlives 2^22 probes (each probe sleeps up to the hint) can only be a protocol bug: trap (the launch fails with a
+// CUDA error) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins == (1u << 22)) __trap();
+    }
 }
 // TMA bulk copy global -> shared (bytes % 16 == 0, both 16-byte aligned), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar) {

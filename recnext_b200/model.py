@@ -27,27 +27,96 @@ from .recconv import _DTYPES, RecConv2d, _stream
 FUSED_FFN = os.environ.get("RECNEXT_FFN", "1") != "0"
 
 
+# RECNEXT_FFN_IMPL=mma keeps the round-1 mma.sync channel-mixer kernel (A/B measurements); default: the tcgen05 kernel
+FFN_IMPL = os.environ.get("RECNEXT_FFN_IMPL", "tc")
+
+
+def ffn_pack(w1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
+    """Packs w1 [hidden, C] and w2 [C, hidden] (16-bit CUDA tensors) into the weight stream of the tcgen05 channel-mixer kernel:
+    128 x 64 tiles in the kernel's consumption order, each stored as the shared-memory image of a K-major tcgen05 operand, so that
+    a tile is one contiguous TMA bulk copy (``recnext_ffn_pack``)."""
+    hid, C = w1.shape
+    if not (w1.is_cuda and w2.is_cuda) or w1.dtype not in (torch.bfloat16, torch.float16) or w2.dtype != w1.dtype or tuple(w2.shape) != (C, hid):
+        raise ValueError(f"ffn_pack: w1 {tuple(w1.shape)} {w1.dtype} / w2 {tuple(w2.shape)} {w2.dtype} must be 16-bit CUDA [hidden, C] / [C, hidden]")
+    with torch.cuda.device(w1.device):
+        nbytes = N.lib().recnext_ffn_packed_bytes(C, hid)
+        if nbytes == 0:
+            raise RuntimeError(f"ffn_pack: C={C} hidden={hid} is not served by the tcgen05 channel-mixer kernel (C % 8 == 0, C <= 768)")
+        packed = torch.empty((nbytes,), dtype=torch.uint8, device=w1.device)
+        N.check(N.lib().recnext_ffn_pack(C, hid, _DTYPES[w1.dtype], w1.contiguous().data_ptr(), w2.contiguous().data_ptr(), packed.data_ptr(),
+                                         _stream(w1)), "recnext_ffn_pack")
+    return packed
+
+
+def ffn_forward_packed(y: torch.Tensor, x: torch.Tensor, packed: torch.Tensor, b1: torch.Tensor, b2: torch.Tensor, hid: int) -> torch.Tensor:
+    """out = x + b2 + W2 gelu(W1 y + b1) with (W1, W2) given as ``ffn_pack(w1, w2)`` (``recnext_ffn_forward_packed``)."""
+    if not (y.is_cuda and x.is_cuda):
+        raise RuntimeError("recnext_b200.ffn_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if y.dtype not in (torch.bfloat16, torch.float16) or x.dtype != y.dtype:
+        raise TypeError("ffn_forward: y and x must share a 16-bit dtype (bfloat16 / float16)")
+    y, x = y.contiguous(), x.contiguous()
+    B, C, H, W = y.shape
+    if tuple(x.shape) != tuple(y.shape) or b1.numel() != hid or b2.numel() != C:
+        raise ValueError(f"ffn_forward: shapes y {tuple(y.shape)} x {tuple(x.shape)} b1 {tuple(b1.shape)} b2 {tuple(b2.shape)} hidden {hid}")
+    out = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        ev = _timing_start()
+        N.check(N.lib().recnext_ffn_forward_packed(B, C, hid, H * W, _DTYPES[y.dtype], y.data_ptr(), x.data_ptr(), packed.data_ptr(),
+                                                   b1.data_ptr(), b2.data_ptr(), out.data_ptr(), _stream(y)), "recnext_ffn_forward_packed")
+        _timing_stop(ev, 3 * y.numel() * y.element_size(), ("ffn",) + tuple(y.shape))
+    return out
+
+
 def ffn_forward(y: torch.Tensor, x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
     """out = x + b2 + W2 gelu(W1 y + b1) per pixel on NCHW tensors — the channel mixer + residual of a RecNeXt block
-    (reference model/recnext.py:125-131,157-158 with every BatchNorm folded) as ONE sm_100a kernel
-    (``recnext_ffn_forward``, include/recnext_b200.h).  16-bit CUDA tensors; no fallback: unsupported shapes raise."""
+    (reference model/recnext.py:125-131,157-158 with every BatchNorm folded) as ONE sm_100a kernel on the tcgen05 tensor
+    cores (``recnext_ffn_pack`` + ``recnext_ffn_forward_packed``, include/recnext_b200.h).  16-bit CUDA tensors; no fallback:
+    unsupported shapes raise."""
     if not (y.is_cuda and x.is_cuda):
         raise RuntimeError("recnext_b200.ffn_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
     if y.dtype not in (torch.bfloat16, torch.float16) or x.dtype != y.dtype or w1.dtype != y.dtype or w2.dtype != y.dtype:
         raise TypeError("ffn_forward: y, x, w1, w2 must share a 16-bit dtype (bfloat16 / float16)")
-    y, x = y.contiguous(), x.contiguous()
     B, C, H, W = y.shape
     hid = w1.shape[0]
     if tuple(w1.shape) != (hid, C) or tuple(w2.shape) != (C, hid) or tuple(x.shape) != tuple(y.shape):
         raise ValueError(f"ffn_forward: shapes y {tuple(y.shape)} x {tuple(x.shape)} w1 {tuple(w1.shape)} w2 {tuple(w2.shape)}")
-    out = torch.empty_like(y)
-    with torch.cuda.device(y.device):
-        ev = _timing_start()
-        N.check(N.lib().recnext_ffn_forward(B, C, hid, H * W, _DTYPES[y.dtype], y.data_ptr(), x.data_ptr(), w1.contiguous().data_ptr(),
-                                            b1.float().contiguous().data_ptr(), w2.contiguous().data_ptr(), b2.float().contiguous().data_ptr(),
-                                            out.data_ptr(), _stream(y)), "recnext_ffn_forward")
-        _timing_stop(ev, 3 * y.numel() * y.element_size(), ("ffn",) + tuple(y.shape))
-    return out
+    if FFN_IMPL == "mma":
+        y, x = y.contiguous(), x.contiguous()
+        out = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            ev = _timing_start()
+            N.check(N.lib().recnext_ffn_forward(B, C, hid, H * W, _DTYPES[y.dtype], y.data_ptr(), x.data_ptr(), w1.contiguous().data_ptr(),
+                                                b1.float().contiguous().data_ptr(), w2.contiguous().data_ptr(), b2.float().contiguous().data_ptr(),
+                                                out.data_ptr(), _stream(y)), "recnext_ffn_forward")
+            _timing_stop(ev, 3 * y.numel() * y.element_size(), ("ffn",) + tuple(y.shape))
+        return out
+    return ffn_forward_packed(y, x, ffn_pack(w1, w2), b1.float().contiguous(), b2.float().contiguous(), hid)
+
+
+def _param_key(*mods) -> tuple:
+    """Identity + version of every parameter / buffer the folded weights are derived from: load_state_dict(), an EMA copy_ or any
+    other in-place update bumps ``_version`` and invalidates the cache."""
+    key = []
+    for m in mods:
+        if m is None:
+            continue
+        for t in list(m.parameters(recurse=False)) + list(m.buffers(recurse=False)):
+            key.append((t.data_ptr(), t._version))
+    return tuple(key)
+
+
+def _needs_autograd(*tensors_and_modules) -> bool:
+    """The fused inference kernels run outside autograd: they are only taken when no gradient can be asked for."""
+    if not torch.is_grad_enabled():
+        return False
+    for o in tensors_and_modules:
+        if isinstance(o, torch.Tensor):
+            if o.requires_grad:
+                return True
+        elif o is not None and any(p.requires_grad for p in o.parameters()):
+            return True
+    return False
+
 
 VARIANTS = {  # reference model/recnext.py:369-406
     "recnext_m0": dict(embed_dim=(40, 80, 160, 320), depth=(2, 2, 9, 1)),
@@ -81,28 +150,6 @@ class DropPath(nn.Module):
         return x * mask.div_(keep)
 
 
-class PointwiseConv2d(nn.Conv2d):
-    """1x1 convolution with the ``nn.Conv2d`` parameters / state_dict, evaluated as ONE batched GEMM on the NCHW
-    tensor: y[b] = W [Cout, Cin] @ x[b] [Cin, H*W] (+ bias).  cuDNN's bf16 1x1 path converts NCHW -> NHWC and back
-    around every call (31 % of the M3 inference step in profiles/r1_launches_bench_step.txt); the RecConv path and
-    BatchNorm want NCHW, so the GEMM is done in that layout instead.  Library GEMM (cuBLAS): plumbing, not a kernel
-    of this repo.  Falls back to F.conv2d for anything that is not a plain contiguous 1x1 case."""
-
-    def forward(self, x):
-        if (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0) and self.groups == 1 and x.dim() == 4
-                and x.is_contiguous() and not torch.jit.is_tracing()):
-            B, C, H, W = x.shape
-            w = self.weight.view(self.out_channels, C)
-            if torch.is_autocast_enabled() and x.is_cuda:
-                dt = torch.get_autocast_dtype("cuda")
-                x, w = x.to(dt), w.to(dt)
-            y = torch.matmul(w, x.view(B, C, H * W))
-            if self.bias is not None:
-                y = y + self.bias.to(y.dtype).view(1, -1, 1)
-            return y.view(B, self.out_channels, H, W)
-        return super().forward(x)
-
-
 class ConvNorm(nn.Sequential):
     """conv (no bias) + BatchNorm2d; ``fuse()`` folds the running statistics into a biased conv."""
 
@@ -118,8 +165,7 @@ class ConvNorm(nn.Sequential):
         shift = bn.bias - scale * bn.running_mean
         if conv.bias is not None:
             shift = shift + scale * conv.bias
-        cls = nn.Conv2d  # (PointwiseConv2d measured slower than cuDNN's path on B200: cuBLAS picks legacy kernels for this layout)
-        out = cls(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
+        out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
                   conv.groups, bias=True, device=conv.weight.device, dtype=conv.weight.dtype)
         out.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
         out.bias.copy_(shift)
@@ -195,7 +241,7 @@ def _fold_mlp(fc1: nn.Conv2d, fc2: nn.Conv2d, dtype, bn: Optional[nn.BatchNorm2d
             b1 = b1 + w1 @ t
             w1 = w1 * s.view(1, -1)
         hid = w1.shape[0]
-        pad = (-hid) % 32
+        pad = (-hid) % 32 if FFN_IMPL == "mma" else 0   # (the tcgen05 kernel pads the hidden width to 128-row chunks itself)
         if pad:
             w1 = torch.cat([w1, w1.new_zeros(pad, w1.shape[1])], 0)
             b1 = torch.cat([b1, b1.new_zeros(pad)], 0)
@@ -203,8 +249,21 @@ def _fold_mlp(fc1: nn.Conv2d, fc2: nn.Conv2d, dtype, bn: Optional[nn.BatchNorm2d
         return w1.to(dtype).contiguous(), b1.contiguous(), w2.to(dtype).contiguous(), b2.contiguous()
 
 
+def _prepare_ffn(w1, b1, w2, b2):
+    """Folded weights -> what the kernel of the selected implementation consumes (the tcgen05 kernel: the packed weight stream)."""
+    if FFN_IMPL == "mma":
+        return ("mma", w1, b1, w2, b2)
+    return ("tc", ffn_pack(w1, w2), b1, b2, w1.shape[0])
+
+
+def _ffn_apply(y, x, prepared):
+    if prepared[0] == "mma":
+        return ffn_forward(y, x, *prepared[1:])
+    return ffn_forward_packed(y, x, *prepared[1:])
+
+
 def _ffn_shape_ok(block: nn.Module, x: torch.Tensor) -> bool:
-    """Does this block (eval mode, ConvNorms folded) take the fused channel-mixer kernel for input x?"""
+    """Does this block (eval mode, ConvNorms folded, no gradient wanted) take the fused channel-mixer kernel for input x?"""
     if block.training or not x.is_cuda or not FUSED_FFN or torch.jit.is_tracing():
         return False
     fc1, fc2 = block.channel_mixer[0], block.channel_mixer[2]
@@ -212,18 +271,21 @@ def _ffn_shape_ok(block: nn.Module, x: torch.Tensor) -> bool:
         return False  # ConvNorms not folded yet (replace_batchnorm / fuse())
     if not isinstance(block.channel_mixer[1], nn.GELU) or getattr(block.channel_mixer[1], "approximate", "none") != "none":
         return False
+    if _needs_autograd(x, block):
+        return False  # a gradient may be asked for (fine-tuning with frozen BN, saliency): the differentiable op chain runs instead
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
     if x.dtype != dt and isinstance(block, Downsample):
         return False
-    C, hid, HW = fc1.in_channels, (fc1.out_channels + 31) // 32 * 32, x.shape[2] * x.shape[3]
-    # measured on B200 (tools/ffn_check.py, batch 256; kernel vs the library path it replaces): [64, 56x56] 0.28 vs 0.78 ms,
-    # [128, 28x28] 0.24 vs 0.41 ms, [256, 14x14] 0.24 vs 0.34 ms (weights staged through shared memory: 192 <= C <= 256 and
-    # C % 32 == 0; [320, 14x14] 0.45 vs 0.43 ms is not worth it yet).  Narrow stages with small images stay on the library
-    # path ([160, 14x14]: 0.46 vs 0.51 ms is a wash)
-    staged = 192 <= C <= 256 and C % 32 == 0 and hid % 32 == 0
-    return (dt in (torch.bfloat16, torch.float16) and C % 16 == 0 and hid % 16 == 0 and HW % 4 == 0
-            and (HW >= 400 or staged or os.environ.get("RECNEXT_FFN") == "all")
-            and (2 * C + hid) * 144 + 64 <= 227 * 1024)
+    C, HW = fc1.in_channels, x.shape[2] * x.shape[3]
+    if dt not in (torch.bfloat16, torch.float16):
+        return False
+    if FFN_IMPL == "mma":
+        hid = (fc1.out_channels + 31) // 32 * 32
+        staged = 192 <= C <= 256 and C % 32 == 0 and hid % 32 == 0
+        return (C % 16 == 0 and hid % 16 == 0 and HW % 4 == 0 and (HW >= 400 or staged or os.environ.get("RECNEXT_FFN") == "all")
+                and (2 * C + hid) * 144 + 64 <= 227 * 1024)
+    # tcgen05 kernel: every RecNeXt width (40 .. 640, hidden 2C or 1.875C) and every plane size
+    return C % 8 == 0 and C <= 768
 
 
 class MetaNeXtBlock(nn.Module):
@@ -241,10 +303,12 @@ class MetaNeXtBlock(nn.Module):
         return super().train(mode)
 
     def _ffn_params(self, dtype, device):
-        """(w1, b1, w2, b2) of the fused channel mixer, eval-mode BatchNorm `norm` folded in; cached until train() is called"""
+        """Folded (and packed) weights of the fused channel mixer, eval-mode BatchNorm `norm` folded in.  Cached; the key holds the
+        version counter of every source tensor, so load_state_dict() / in-place updates are picked up."""
+        key = (dtype, device, _param_key(self.channel_mixer[0], self.channel_mixer[2], self.norm))
         c = getattr(self, "_ffn_cache", None)
-        if c is None or c[0] != (dtype, device):
-            c = ((dtype, device), _fold_mlp(self.channel_mixer[0], self.channel_mixer[2], dtype, self.norm))
+        if c is None or c[0] != key:
+            c = (key, _prepare_ffn(*_fold_mlp(self.channel_mixer[0], self.channel_mixer[2], dtype, self.norm)))
             self._ffn_cache = c
         return c[1]
 
@@ -255,7 +319,7 @@ class MetaNeXtBlock(nn.Module):
         if self._ffn_eligible(x):
             # token mixer (sm_100a RecConv kernel) -> ONE fused kernel for norm + 1x1 conv + GELU + 1x1 conv + residual
             y = self.token_mixer(x)
-            return ffn_forward(y, x.to(y.dtype), *self._ffn_params(y.dtype, y.device))
+            return _ffn_apply(y, x.to(y.dtype), self._ffn_params(y.dtype, y.device))
         return x + self.drop_path(self.channel_mixer(self.norm(self.token_mixer(x))))
 
 
@@ -276,11 +340,12 @@ class MetaNeXtBlockA(nn.Module):
     def forward(self, x):
         if _ffn_shape_ok(self, x):
             y = self.token_mixer(x)
+            key = (y.dtype, y.device, _param_key(self.channel_mixer[0], self.channel_mixer[2]))
             c = getattr(self, "_ffn_cache", None)
-            if c is None or c[0] != (y.dtype, y.device):
-                c = ((y.dtype, y.device), _fold_mlp(self.channel_mixer[0], self.channel_mixer[2], y.dtype))
+            if c is None or c[0] != key:
+                c = (key, _prepare_ffn(*_fold_mlp(self.channel_mixer[0], self.channel_mixer[2], y.dtype)))
                 self._ffn_cache = c
-            return ffn_forward(y, x.to(y.dtype), *c[1])
+            return _ffn_apply(y, x.to(y.dtype), c[1])
         return x + self.drop_path(self.channel_mixer(self.token_mixer(x)))
 
 
@@ -297,32 +362,34 @@ class Downsample(nn.Module):
         return super().train(mode)
 
     def _dw_params(self, device):
+        key = (device, _param_key(self.token_mixer, self.norm))
         c = getattr(self, "_dw_cache", None)
-        if c is None or c[0] != device:
+        if c is None or c[0] != key:
             conv, bn = self.token_mixer, self.norm
             with torch.no_grad():
                 s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
                 t = (bn.bias - s * bn.running_mean).float()
                 w = (conv.weight.float() * s.view(-1, 1, 1, 1)).contiguous()
                 b = (s * conv.bias.float() + t).contiguous() if conv.bias is not None else t.contiguous()
-            c = (device, (w, b))
+            c = (key, (w, b))
             self._dw_cache = c
         return c[1]
 
     def forward(self, x):
         dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         if (not self.training and x.is_cuda and FUSED_FFN and dt in (torch.bfloat16, torch.float16) and not torch.jit.is_tracing()
-                and (x.shape[2] + 8) * (x.shape[3] + 9) * 4 + 448 <= 227 * 1024):
+                and not _needs_autograd(x, self) and (x.shape[2] + 8) * (x.shape[3] + 9) * 4 + 448 <= 227 * 1024):
             x = dwdown_forward(x.to(dt), *self._dw_params(x.device))   # norm(token_mixer(x)): one kernel, BatchNorm folded
         else:
             x = self.norm(self.token_mixer(x))
         if _ffn_shape_ok(self, x):
             # x + mlp(x) (model/recnext.py:145-146) as the same fused kernel: the mixer input is also the residual
+            key = (x.dtype, x.device, _param_key(self.channel_mixer[0], self.channel_mixer[2]))
             c = getattr(self, "_ffn_cache", None)
-            if c is None or c[0] != (x.dtype, x.device):
-                c = ((x.dtype, x.device), _fold_mlp(self.channel_mixer[0], self.channel_mixer[2], x.dtype))
+            if c is None or c[0] != key:
+                c = (key, _prepare_ffn(*_fold_mlp(self.channel_mixer[0], self.channel_mixer[2], x.dtype)))
                 self._ffn_cache = c
-            return ffn_forward(x, x, *c[1])
+            return _ffn_apply(x, x, c[1])
         return x + self.channel_mixer(x)
 
 

@@ -30,13 +30,22 @@ def test_bn_fold_into_first_conv_cpu():
     with torch.no_grad():
         ref = blk.channel_mixer[0](blk.norm(y))            # ConvNorm(BN(y))
         replace_batchnorm(blk)
-        w1, b1, w2, b2 = blk._ffn_params(torch.float32, torch.device("cpu"))
+        import recnext_b200.model as M
+        w1, b1, w2, b2 = M._fold_mlp(blk.channel_mixer[0], blk.channel_mixer[2], torch.float32, blk.norm)
         got = F.conv2d(y, w1.view(64, 32, 1, 1), b1)
         assert rel_err(got.numpy(), ref.numpy()) < 1e-5
         assert tuple(w2.shape) == (32, 64) and tuple(b2.shape) == (32,)
     assert not blk._ffn_eligible(y)                        # CPU tensors never take the kernel (and nothing falls back silently)
     blk.train()
     assert blk._ffn_cache is None                          # cached fold is dropped when the statistics may change
+    # the cache key carries the version counter of every source tensor: load_state_dict / in-place updates invalidate it
+    k0 = M._param_key(blk.channel_mixer[0], blk.channel_mixer[2], blk.norm)
+    blk.load_state_dict(blk.state_dict())
+    assert M._param_key(blk.channel_mixer[0], blk.channel_mixer[2], blk.norm) != k0
+    # with gradients enabled and trainable parameters the inference kernels step aside (they run outside autograd)
+    assert M._needs_autograd(y, blk)
+    with torch.no_grad():
+        assert not M._needs_autograd(y, blk)
 
 
 def test_ffn_forward_has_no_cpu_path():
@@ -46,15 +55,22 @@ def test_ffn_forward_has_no_cpu_path():
         ffn_forward(torch.randn(1, 16, 4, 4), torch.randn(1, 16, 4, 4), torch.randn(32, 16), torch.randn(32), torch.randn(16, 32), torch.randn(16))
 
 
+# (B, C, H, W, hidden): every RecNeXt width of the M / A series (reference model/recnext.py:369-406, model/recattn.py:382-419; hidden = 2C
+# or 1.875C) at its stage's plane size, plus ragged cases: pixel tiles that straddle images, HW % 8 != 0 (8- and 2-byte accesses),
+# C % 16 != 0 (zero-padded K), hidden % 128 != 0, more tiles than SMs
+_FFN_CASES = [(4, 64, 56, 56, 128), (4, 128, 28, 28, 256), (3, 256, 14, 14, 512), (3, 512, 7, 7, 1024), (3, 80, 28, 28, 160), (2, 160, 14, 14, 320),
+              (5, 320, 14, 14, 640), (3, 640, 7, 7, 1280), (2, 40, 56, 56, 80), (2, 64, 56, 56, 120), (2, 128, 28, 28, 240), (2, 32, 6, 6, 64),
+              (2, 48, 10, 18, 96), (3, 24, 5, 7, 40), (64, 64, 56, 56, 128), (2, 256, 50, 84, 512)]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(4, 64, 56, 56), (4, 128, 28, 28), (3, 256, 14, 14), (3, 80, 28, 28), (2, 160, 14, 14), (2, 32, 6, 6), (2, 48, 10, 18)],
-                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("case", _FFN_CASES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
-def test_ffn_kernel_vs_torch(shape, dtype):
+def test_ffn_kernel_vs_torch(case, dtype):
     from recnext_b200.model import ffn_forward
 
-    B, C, H, W = shape
-    hid = 2 * C
+    B, C, H, W, hid = case
+    shape = (B, C, H, W)
     torch.manual_seed(C + H)
     y = torch.randn(shape, device="cuda").to(dtype); x = torch.randn(shape, device="cuda").to(dtype)
     w1 = (torch.randn(hid, C, device="cuda") * C ** -0.5).to(dtype); w2 = (torch.randn(C, hid, device="cuda") * hid ** -0.5).to(dtype)
@@ -62,16 +78,20 @@ def test_ffn_kernel_vs_torch(shape, dtype):
     out = ffn_forward(y, x, w1, b1, w2, b2)
     ref = x.float() + F.conv2d(F.gelu(F.conv2d(y.float(), w1.float().view(hid, C, 1, 1), b1)), w2.float().view(C, hid, 1, 1), b2)
     assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < (TOL_BF16 if dtype == torch.bfloat16 else 4e-3)
+    # the kernel is deterministic and every pixel is independent: a batch slice gives bit-identical rows
+    assert torch.equal(out, ffn_forward(y, x, w1, b1, w2, b2))
+    if B > 1:
+        assert torch.equal(out[1:], ffn_forward(y[1:].contiguous(), x[1:].contiguous(), w1, b1, w2, b2))
 
 
 @pytest.mark.gpu
 def test_ffn_unsupported_shapes_are_errors():
     from recnext_b200.model import ffn_forward
 
-    y = torch.randn(1, 40, 7, 7, device="cuda").bfloat16()   # C % 16 != 0 and HW % 4 != 0
-    with pytest.raises(RuntimeError, match="recnext_ffn_forward"):
-        ffn_forward(y, y, torch.randn(80, 40, device="cuda").bfloat16(), torch.randn(80, device="cuda"), torch.randn(40, 80, device="cuda").bfloat16(),
-                    torch.randn(40, device="cuda"))
+    y = torch.randn(1, 36, 7, 7, device="cuda").bfloat16()   # C % 8 != 0
+    with pytest.raises(RuntimeError, match="ffn_pack"):
+        ffn_forward(y, y, torch.randn(72, 36, device="cuda").bfloat16(), torch.randn(72, device="cuda"), torch.randn(36, 72, device="cuda").bfloat16(),
+                    torch.randn(36, device="cuda"))
 
 
 @pytest.mark.gpu

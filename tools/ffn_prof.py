@@ -1,12 +1,38 @@
-"""One fused-FFN launch for ncu.  python tools/ffn_prof.py B C H"""
-import os, sys, torch
+"""One shape of the fused channel mixer, a few launches (for ncu):   python tools/ffn_prof.py B C H [hidden] [reps]"""
+import os, sys
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from recnext_b200.model import ffn_forward
+from recnext_b200.model import ffn_pack, ffn_forward_packed
 B, C, H = (int(v) for v in sys.argv[1:4])
-hid = 2 * C
-y = torch.randn(B, C, H, H, device="cuda").bfloat16(); x = torch.randn_like(y)
-w1 = (torch.randn(hid, C, device="cuda") * C ** -0.5).bfloat16(); w2 = (torch.randn(C, hid, device="cuda") * hid ** -0.5).bfloat16()
-b1 = torch.randn(hid, device="cuda") * 0.1; b2 = torch.randn(C, device="cuda") * 0.1
-for _ in range(2):
-    ffn_forward(y, x, w1, b1, w2, b2)
-torch.cuda.synchronize()
+hid = int(sys.argv[4]) if len(sys.argv) > 4 else 2 * C
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+dev = "cuda"
+torch.manual_seed(0)
+y = torch.randn(B, C, H, H, device=dev).bfloat16(); x = torch.randn(B, C, H, H, device=dev).bfloat16()
+w1 = (torch.randn(hid, C, device=dev) * C ** -0.5).bfloat16(); w2 = (torch.randn(C, hid, device=dev) * hid ** -0.5).bfloat16()
+b1 = torch.randn(hid, device=dev) * 0.1; b2 = torch.randn(C, device=dev) * 0.1
+pk = ffn_pack(w1, w2)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ts = []
+for _ in range(reps):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); ffn_forward_packed(y, x, pk, b1, b2, hid); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+print(f"[{B},{C},{H},{H}] hid {hid}: {sorted(ts)[len(ts)//2]:.4f} ms")
+if os.environ.get("RECNEXT_FFN_PROF"):
+    import ctypes, numpy as np
+    from recnext_b200 import _native as N
+    buf = np.zeros(2048, dtype=np.int64)
+    N.lib().recnext_debug_prof.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    N.lib().recnext_debug_prof.restype = ctypes.c_int
+    rc = N.lib().recnext_debug_prof(buf.ctypes.data, 2048)
+    print('debug_prof rc', rc, 'nonzero', int((buf != 0).sum()), 'min', buf.min(), 'max', buf.max())
+    t0 = buf[buf != 0].min()
+    m, e, l = buf[0:512], buf[512:1024], buf[1536:2048]
+    rel = lambda v: int(v - t0) if v != 0 else -1
+    print("MMA warp  : g: G1 start, G1 issued, G2 start (H_FULL seen), G2 issued")
+    for g in range(12): print(f"  {g:3d}: " + "  ".join(f"{rel(m[4*g+i]):7d}" for i in range(4)))
+    print("epilogue w0: g: iter start, D1_FULL seen, H_FULL arrived, D2_FULL seen (epi2 of previous tile), epi2 done")
+    for g in range(12): print(f"  {g:3d}: " + "  ".join(f"{rel(e[6*g+i]):7d}" for i in range(5)))
+    print("loader w10: t: Y_EMPTY seen, Y_FULL arrived")
+    for t in range(8): print(f"  {t:3d}: " + "  ".join(f"{rel(l[2*t+i]):7d}" for i in range(2)))

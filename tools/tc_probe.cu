@@ -144,6 +144,45 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int N, int nrep, int mode,
         }
         t1 = clock64();
         if (lane == 0) { res[warp * 4 + 0] = t1 - t0; res[warp * 4 + 1] = acc; res[warp * 4 + 2] = 1; }
+    } else if (mode == 5 || mode == 6 || mode == 7) {
+        // mode 5: MN-major B, idle neighbours; mode 6: warps 1-3 stream 16-byte stores into an unrelated region meanwhile;
+        // mode 7: warps 1-3 stream 16-byte LOADS meanwhile
+        const uint32_t idesc_mn = tc::make_idesc(128, N, 1, 0, 1);
+        const uint64_t bdm = tc::make_sdesc(tc::smem_u32(smem + kAImg), 128, 64 * 16 + 16);
+        __shared__ volatile int stop;
+        if (tid == 0) stop = 0;
+        __syncthreads();
+        if (uwarp == 0) {
+            uint32_t elected = 0;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+            t0 = clock64();
+            for (int i = 0; i < nrep; ++i) {
+                const uint64_t a_i = tc::sdesc_advance(ad, (i & 3) * 4096);
+                const uint64_t b_i = tc::sdesc_advance(bdm, (i & 3) * 256);
+                if (elected) tc::mma_ss(tbase + (i & 1) * N, a_i, b_i, idesc_mn, 1);
+            }
+            if (elected) tc::mma_commit(bar0);
+            t1 = clock64();
+            bool ok = false;
+            for (int it = 0; it < (1 << 24); ++it) if (tc::mbar_try_wait(bar0, 0)) { ok = true; break; }
+            t2 = clock64();
+            if (lane == 0) { res[0] = t1 - t0; res[1] = t2 - t0; res[2] = ok ? 1 : 0; stop = 1; }
+        } else if (mode != 5) {
+            uint4* reg = reinterpret_cast<uint4*>(smem + kAImg + 80 * 1024) + (warp - 1) * 32 * 8 + lane;
+            uint4 v = make_uint4(tid, 1, 2, 3);
+            long long n = 0;
+            while (!stop) {
+                if (mode == 6) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) reg[u * 32] = v;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { uint4 w = reg[u * 32]; v.x ^= w.x; }
+                }
+                n += 8;
+            }
+            if (lane == 0) res[warp * 4 + 3] = n + (v.x & 1);
+        }
     } else if (mode == 3) {
         if (tid == 0) {
             t0 = clock64();
@@ -284,7 +323,8 @@ int main() {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("[%s] KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(4); }
         long long r[16]; CK(cudaMemcpy(r, dres, sizeof r, cudaMemcpyDeviceToHost));
-        if (mode == 0 || mode == 3) printf("[time %s] N=%d nrep=%d issue=%lld cyc total=%lld cyc (%.1f / MMA) ok=%lld\n", name, N, nrep, r[0], r[1] ? r[1] : r[0], (double)(r[1] ? r[1] : r[0]) / nrep, r[2]);
+        if (mode >= 5) printf("[time %s] N=%d nrep=%d total=%lld cyc (%.1f / MMA) ok=%lld  neighbour 16-byte accesses per warp: %lld %lld %lld (%.1f B/cyc)\n", name, N, nrep, r[1], (double)r[1] / nrep, r[2], r[7], r[11], r[15], 16.0 * 32 * (r[7] + r[11] + r[15]) / (double)r[1]);
+        else if (mode == 0 || mode == 3) printf("[time %s] N=%d nrep=%d issue=%lld cyc total=%lld cyc (%.1f / MMA) ok=%lld\n", name, N, nrep, r[0], r[1] ? r[1] : r[0], (double)(r[1] ? r[1] : r[0]) / nrep, r[2]);
         else if (mode == 1) printf("[time %s] N=%d nrep=%d x2 issuers: w0 total=%lld w1 total=%lld (%.1f cyc / MMA overall) ok=%lld,%lld\n", name, N, nrep, r[1], r[5], (double)(r[1] > r[5] ? r[1] : r[5]) / (2.0 * nrep), r[2], r[6]);
         else printf("[time %s] cols=%d nrep=%d per-warp cycles %lld %lld %lld %lld -> %.1f B/cyc/SM\n", name, N, nrep, r[0], r[4], r[8], r[12], 4.0 * 32 * N * 4 * nrep / (double)r[0]);
     };
@@ -297,6 +337,11 @@ int main() {
         timeit("mma_n256", 256, 512, 0, 128, 2048);
         timeit("two_issuers_n16", 16, 2048, 1, 128, 2048);
         timeit("two_issuers_n128", 128, 1024, 1, 128, 2048);
+        timeit("mma_n128_mnB", 128, 1024, 5, 128, 2048);
+        timeit("mma_n128_mnB_plus_sts", 128, 1024, 6, 128, 2048);
+        timeit("mma_n128_mnB_plus_lds", 128, 1024, 7, 128, 2048);
+        timeit("mma_n256_mnB", 256, 512, 5, 128, 2048);
+        timeit("mma_n256_mnB_plus_sts", 256, 512, 6, 128, 2048);
         timeit("tmem_ld", 512, 64, 2, 128, 2048);
         timeit("tmem_ld_pipelined4", 512, 64, 4, 128, 2048);
         timeit("roundtrip_n16", 16, 256, 3, 128, 2048);
