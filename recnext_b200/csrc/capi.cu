@@ -10,6 +10,7 @@
 #include "recconv_body.cuh"
 #include "wplan.h"
 #include "mplan.h"
+#include "mbplan.h"
 #include "gstream.h"
 #include "ffn_tc.h"
 #include "devcfg.h"
@@ -17,6 +18,7 @@
 
 namespace recnext {
 cudaError_t m_launch(const MPlan&, const KernelArgs&, cudaStream_t);  // recconv_m5.cu: tensor-core forward
+cudaError_t mb_launch(const MBPlan&, const KernelArgs&, float* gw, float* gb, cudaStream_t);  // recconv_mb5.cu: tensor-core backward
 bool m_static_geometry(const MPlan&);
 struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ, staged, offW, kc; };  // ffn_mma.cu
 int ffn_make_plan(FfnPlan&, int B, int C, int HID, int HW, int dtype);
@@ -150,6 +152,25 @@ static int make_plan(const recconv_desc* d, bool bwd, Plan& pl) {
     if (rc == 1) return 1;
     if (rc) return fail(RECNEXT_EINVAL, "recconv: bad arguments");
     return 0;
+}
+static bool fma_forced();
+// 0: tensor-core backward plan made (16-bit activations, k = 5, the plane's four pyramid sets fit on chip); 1: not eligible
+static int make_wplan(const recconv_desc* d, bool bwd, WPlan& pl);
+static int make_mbplan(const recconv_desc* d, MBPlan& bp) {
+    if (fma_forced() || d->k != 5 || !(d->dtype == RECNEXT_BF16 || d->dtype == RECNEXT_F16)) return 1;
+    // planes below 20 x 20: the many tiny stages of the tensor-core schedule are pure latency and the FMA kernel, which packs
+    // several planes into a warp, is as fast or faster (measured [256,256,14,14]: 0.86 ms FMA vs 0.90 ms); RECNEXT_PATH=mma overrides
+    {
+        const char* e = getenv("RECNEXT_PATH");
+        WPlan wp;
+        if (!(e && strcmp(e, "mma") == 0) && d->H * d->W < 400 && make_wplan(d, true, wp) == 0) return 1;
+    }
+    MBPlanOptions opt;
+    opt.num_sms = device_sms();
+    if (const char* e = getenv("RECNEXT_MBG")) opt.force_G = atoi(e);
+    if (const char* e = getenv("RECNEXT_MBTW")) opt.force_TW = atoi(e);
+    if (const char* e = getenv("RECNEXT_MBNT")) opt.force_NT = atoi(e);
+    return mb_make_plan(bp, d->B, d->C, d->H, d->W, d->k, d->level, d->mode, d->dtype, d->wdtype, d->has_bias, opt) == 0 ? 0 : 1;
 }
 static GStreamDesc stream_desc(const recconv_desc* d) {
     GStreamDesc g;
@@ -427,6 +448,8 @@ RECNEXT_API int recnext_ffn_forward_packed(int32_t B, int32_t C, int32_t hidden,
 RECNEXT_API size_t recconv_backward_workspace_bytes(const recconv_desc* d) {
     if (check_desc(d)) return 0;
     if (d->B == 0 || d->C == 0) return 0;
+    MBPlan bp;
+    if (!stream_forced() && make_mbplan(d, bp) == 0) return (size_t)bp.ws_floats * sizeof(float);
     WPlan wp;
     if (!stream_forced() && make_wplan(d, true, wp) == 0) return (size_t)wp.ws_partial_floats * sizeof(float);
     Plan pl;
@@ -457,6 +480,18 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
     Plan pl;
     int n_partials = 0, wstride = 0;
     cudaError_t e;
+    MBPlan bp;
+    if (!stream_forced() && (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gx) & 3) == 0 && make_mbplan(d, bp) == 0) {
+        // 16-bit activations, k = 5: the tensor-core backward (mbwd.cuh) writes gw / gb through its own deterministic finalize
+        const size_t need = (size_t)bp.ws_floats * sizeof(float);
+        if (!workspace || workspace_bytes < need)
+            return fail(RECNEXT_EWORKSPACE, "recconv_backward: workspace %zu bytes < %zu needed", workspace_bytes, need);
+        a.prof = prof_buffer();
+        if ((((uintptr_t)x | (uintptr_t)gy) & 15) != 0) bp.use_tma = 0;   // bulk copies need 16-byte aligned sources
+        e = mb_launch(bp, a, gw, gb, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recconv_backward(mma): %s", cudaGetErrorString(e));
+        return RECNEXT_OK;
+    }
     if (!stream_forced() && make_wplan(d, true, wp) == 0) {
         const size_t need = (size_t)wp.ws_partial_floats * sizeof(float);
         if (!workspace || workspace_bytes < need)
@@ -510,6 +545,14 @@ RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char*
                  "plane=%d B frag-regs/channel=%d tma=%d geometry=%s",
                  mp.L, mp.B, mp.C, mp.H, mp.W, mp.G, mp.TW, mp.NTEAM, mp.threads, mp.grid, mp.smem_bytes, mp.team_bytes, mp.l0_bytes + mp.upper_bytes,
                  mp.nregs, mp.use_tma, m_static_geometry(mp) ? "compile-time" : "run-time");
+        return RECNEXT_OK;
+    }
+    MBPlan bp;
+    if (!stream_forced() && backward && make_mbplan(d, bp) == 0) {
+        snprintf(buf, buflen,
+                 "bwd tensor-core k=5 L=%d [%d,%d,%d,%d] planes/batch=%d warps/team=%d teams/CTA=%d threads=%d grid=%d smem=%d B team=%d B "
+                 "frag-regs/channel=%d tma=%d",
+                 bp.f.L, bp.f.B, bp.f.C, bp.f.H, bp.f.W, bp.f.G, bp.f.TW, bp.f.NTEAM, bp.f.threads, bp.grid, bp.smem_bytes, bp.team_bytes, bp.nregs, bp.use_tma);
         return RECNEXT_OK;
     }
     WPlan wp;
