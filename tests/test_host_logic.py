@@ -230,7 +230,7 @@ def test_team_plan_covers_every_plane_exactly_once():
 
 def test_tensor_core_plan_selection(native):
     """16-bit activations with k = 5 take the tensor-core forward (compile-time geometry for the RecNeXt stage shapes);
-    fp32, k != 5, tiny planes and the backward stay on the FMA kernels."""
+    fp32, k != 5 and tiny planes stay on the FMA kernels; the 16-bit backward of planes >= 20 x 20 is tensor-core too."""
     import torch
 
     from recnext_b200 import recconv
@@ -244,7 +244,12 @@ def test_tensor_core_plan_selection(native):
     assert "tensor-core" not in d((256, 512, 7, 7), 1, torch.bfloat16)      # smaller than one MMA tile
     assert "tensor-core" not in d((256, 64, 56, 56), 4, torch.float32)
     assert "tensor-core" not in d((4, 64, 56, 56), 4, torch.bfloat16, k=7)
-    assert "tensor-core" not in d((4, 64, 56, 56), 4, torch.bfloat16, bwd=True)
+    # backward: tensor-core kernel for 16-bit planes of at least 20 x 20 (smaller ones pack several planes per warp in the FMA kernel)
+    assert "bwd tensor-core" in d((4, 64, 56, 56), 4, torch.bfloat16, bwd=True)
+    assert "bwd tensor-core" in d((2, 128, 100, 168), 3, torch.bfloat16, bwd=True)       # detection stage 1 fits on chip in 16 bits
+    assert "tensor-core" not in d((256, 256, 14, 14), 2, torch.bfloat16, bwd=True)
+    assert "tensor-core" not in d((4, 64, 56, 56), 4, torch.float32, bwd=True)
+    assert "streamed" in d((2, 64, 200, 336), 4, torch.bfloat16, bwd=True)               # detection stage 0: level by level
     # teams fill the SM: at least 8 warps for every stage shape
     import re
     for shape, L in [((256, 64, 56, 56), 4), ((256, 128, 28, 28), 3), ((256, 256, 14, 14), 2), ((2, 128, 100, 168), 3)]:
