@@ -7,8 +7,15 @@
 A step = one forward pass of the fused-BN eval RecNeXt-M3 over a synthetic batch of 256 images (224x224, bf16
 autocast) per GPU; every RecConv2d token mixer runs the fused sm_100a kernel through the C ABI.  Inference
 shards by batch with no data-path collective (replicas, "weak" scaling: 256 images per GPU).
-Prints ONE JSON line (rank 0).  `--impl reference` times the reference's PyTorch CPU path (oracle/torch_ref.py
-restatement — the reference itself is pure Python and is not present on the GPU box) on the host cores.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own PyTorch CPU path on the host cores: the UNMODIFIED
+reference model code staged by oracle/make_ref.py into oracle/_ref (kind "reference"), or the restatement in oracle/torch_ref.py when
+that staging is absent (kind "port").
+
+Beside the contract keys the line carries the other BASELINE.json configs as extra objects that do not disturb `value`:
+`recconv_fwd_bwd` (the second half of the metric), `train_ddp` (configs[2]: RecNeXt-M5 fwd + bwd + AdamW, DDP under torchrun),
+`a_series` (configs[3]: RecNeXt-A3 inference), `detection` (configs[4]: M3 backbone fwd + bwd at 800 x 1344, 2 images per GPU),
+`gpu_eager_baseline` (the reference model in PyTorch eager on the same GPU: what a user gets today) and, in `cpu_baseline`,
+configs[0] (RecNeXt-M0, batch 1, fp32 CPU).
 """
 from __future__ import annotations
 
@@ -91,21 +98,32 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz)}
 
 
-def build_cpu_reference_model():
-    """The reference's CPU path: same model definition with the PyTorch-eager RecConv2d restatement (fp32, eval,
-    BN folded) — what a user of the reference gets on the host."""
+def build_reference_model(variant: str, device="cpu"):
+    """-> (fused-BN eval model, kind).  kind "reference": the UNMODIFIED reference code (oracle/_ref, staged by oracle/make_ref.py:
+    model/recnext.py + model/recattn.py + utils.replace_batchnorm, speed_gpu.py:47-50) behind the timm stand-in; kind "port": the
+    restatement oracle/torch_ref.py inside this repo's model definition (same ATen kernels) when the staging is absent."""
     import torch
 
+    torch.manual_seed(0)
+    try:
+        from oracle.make_ref import available, import_reference
+
+        if available():
+            create_model, replace_bn = import_reference()
+            net = create_model(variant).eval()
+            replace_bn(net)
+            return net.to(device), "reference"
+    except Exception as ex:  # fall through to the port, and say so
+        sys.stderr.write(f"bench: oracle/_ref unusable ({ex}); timing the port\n")
     from oracle.torch_ref import RefRecAttn2d, RefRecConv2d
     from recnext_b200.model import create_model, replace_batchnorm
 
-    torch.manual_seed(0)
-    net = create_model(MODEL, token_mixer=RefRecAttn2d if "_a" in MODEL else RefRecConv2d).eval()
+    net = create_model(variant, token_mixer=RefRecAttn2d if "_a" in variant else RefRecConv2d).eval()
     replace_batchnorm(net)
-    return net
+    return net.to(device), "port"
 
 
-def cpu_reference_rate(steps: int, warmup: int, batch: int):
+def cpu_reference_rate(steps: int, warmup: int, batch: int, variant: str = None):
     """images/sec of the reference CPU path on `batch` images per step, all host threads."""
     import torch
 
@@ -114,7 +132,7 @@ def cpu_reference_rate(steps: int, warmup: int, batch: int):
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         torch.set_num_threads(max(1, os.cpu_count() or 1))
-    net = build_cpu_reference_model()
+    net, kind = build_reference_model(variant or MODEL)
     x = torch.randn(batch, 3, RES, RES)
     ts = []
     with torch.no_grad():
@@ -125,20 +143,24 @@ def cpu_reference_rate(steps: int, warmup: int, batch: int):
             if i >= warmup:
                 ts.append(dt)
     total = sum(ts)
-    return batch * len(ts) / total, total / len(ts) * 1e3, torch.get_num_threads()
+    return batch * len(ts) / total, total / len(ts) * 1e3, torch.get_num_threads(), kind
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    batch = 16
-    rate, ms, threads = cpu_reference_rate(args.steps, min(args.warmup, 2), batch)
-    sample = f"{batch} images/step of the same model (fp32, eval, BN folded, PyTorch CPU eager, {threads} threads)"
+    batch = 64   # as close to the metric's 256 as keeps a step near one second on a 16-thread host
+    warm = min(args.warmup, 2)
+    rate, ms, threads, kind = cpu_reference_rate(args.steps, warm, batch)
+    what = "UNMODIFIED reference code (oracle/_ref)" if kind == "reference" else "restatement oracle/torch_ref.py"
+    sample = f"{batch} images/step of the same model (fp32, eval, BN folded, PyTorch CPU eager, {threads} threads; {what})"
+    m0_rate, m0_ms, _, _ = cpu_reference_rate(5, 2, 1, "recnext_m0")   # BASELINE.json configs[0]
     out = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU sample: " + sample},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "configs0_m0_batch1_fp32": {"images_per_s": m0_rate, "ms_per_image": m0_ms}},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -233,6 +255,132 @@ def recconv_microbench(torch, R, peak):
     return {"achieved_gbs": round(agg, 1), "frac_of_hbm_peak": round(agg / peak, 4), "per_stage": res}
 
 
+def _time_steps(torch, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def run_extras(args, rank, world, dev, peak):
+    """The other BASELINE.json configs, measured after the metric (extra objects of the JSON line; none of them touches `value`).
+    train_ddp runs on every rank (its gradient all-reduce is a collective); the rest on rank 0 only."""
+    import torch
+    import torch.nn.functional as F
+
+    from recnext_b200 import dist as D
+    from recnext_b200.model import create_model, replace_batchnorm
+
+    out = {}
+    # ---- configs[2]: RecNeXt-M5 training step (fwd + bwd + AdamW, bf16 autocast), 128 images per GPU, DDP under torchrun
+    try:
+        torch.manual_seed(0)
+        net = create_model("recnext_m5", drop_path=0.0).to(dev).train()
+        ddp = world > 1
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True, static_graph=True) if ddp else net
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True)
+        tb = 128
+        x = torch.randn(tb, 3, RES, RES, device=dev)
+        tgt = torch.randint(0, 1000, (tb,), device=dev)
+
+        def train_step(sync=True):
+            opt.zero_grad(set_to_none=True)
+            ctx = model.no_sync() if (ddp and not sync) else _null()
+            with ctx:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = F.cross_entropy(model(x).float(), tgt)
+                loss.backward()
+            opt.step()
+
+        D.barrier(dev)
+        ms = D.max_over_ranks(_time_steps(torch, train_step, 4, 2), dev)
+        ms_local = D.max_over_ranks(_time_steps(torch, lambda: train_step(False), 3, 1), dev) if ddp else ms
+        grad_mb = sum(p.numel() for p in net.parameters()) * 4 / 1e6
+        out["train_ddp"] = {"config": "BASELINE.json configs[2]: RecNeXt-M5 training step (fwd + bwd + fused AdamW), bf16 autocast, 128 images per GPU",
+                            "images_per_s": tb * world / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world, "global_batch": tb * world,
+                            "ms_per_step_without_allreduce": ms_local, "exposed_allreduce_ms": max(ms - ms_local, 0.0), "gradient_mbytes_fp32": round(grad_mb, 1),
+                            "collective": "DDP bucketed gradient all-reduce over NCCL (gradient_as_bucket_view, static_graph), overlapped with backward" if ddp else "none (1 GPU)",
+                            "kernels": "RecConv2d: sm_100a tensor-core forward + backward (16-bit); BatchNorm / 1x1 convs / optimizer: PyTorch in training mode"}
+        del model, net, opt, x
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["train_ddp"] = {"error": str(ex)[:300]}
+    D.barrier(dev)
+    if rank != 0:
+        return out
+    # ---- configs[3]: RecNeXt-A3 inference (linear attention + nearest interpolation), batch 256
+    try:
+        torch.manual_seed(0)
+        a3 = create_model("recnext_a3").eval()
+        replace_batchnorm(a3)
+        a3.to(dev)
+        xa = torch.randn(BATCH, 3, RES, RES, device=dev).bfloat16()
+
+        def a3_step():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                a3(xa)
+
+        ms = _time_steps(torch, a3_step, 8, 3)
+        out["a_series"] = {"config": "BASELINE.json configs[3]: RecNeXt-A3 inference, batch 256 at 224x224 bf16, fused-BN eval model", "images_per_s": BATCH / (ms * 1e-3),
+                           "ms_per_step": ms, "n_gpus": 1}
+        del a3, xa
+    except Exception as ex:
+        out["a_series"] = {"error": str(ex)[:300]}
+    # ---- configs[4]: RecNeXt-M3 backbone forward + backward at detection scale (800 x 1333 padded to 800 x 1344), 2 images per GPU, frozen BatchNorm
+    try:
+        torch.manual_seed(0)
+        det = create_model("recnext_m3").eval().to(dev)   # eval(): BatchNorm frozen as in detection fine-tuning; gradients flow to every conv
+        xd = torch.randn(2, 3, 800, 1344, device=dev, requires_grad=True)
+
+        def det_step():
+            for p_ in det.parameters():
+                p_.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                f = det.forward_features(xd)
+            f.float().mean().backward()
+
+        ms = _time_steps(torch, det_step, 3, 2)
+        out["detection"] = {"config": "BASELINE.json configs[4]: RecNeXt-M3 backbone fwd + bwd at 800x1344 (RecConv level 4 at stage 0), 2 images per GPU, bf16 autocast",
+                            "images_per_s": 2 / (ms * 1e-3), "ms_per_step": ms, "n_gpus": 1,
+                            "recconv_paths": "stage 0 (200x336): tensor-core forward, streamed backward; stage 1 (100x168) and below: tensor-core forward and backward on chip"}
+        del det, xd
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["detection"] = {"error": str(ex)[:300]}
+    # ---- what a user of the reference gets on this GPU today: the reference model in PyTorch eager (cuDNN / ATen), same config as the metric
+    try:
+        ref, kind = build_reference_model(MODEL, dev)
+        xr = torch.randn(BATCH, 3, RES, RES, device=dev).bfloat16()
+        torch.backends.cudnn.benchmark = True
+
+        def ref_step():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                ref(xr)
+
+        ms = _time_steps(torch, ref_step, 5, 3)
+        out["gpu_eager_baseline"] = {"config": WORKLOAD + " — PyTorch eager on the same GPU", "images_per_s": BATCH / (ms * 1e-3), "ms_per_step": ms,
+                                     "kind": kind, "note": "cudnn.benchmark=True as in the reference harness (main.py:213); 4L+2 launches per RecConv2d, every intermediate through HBM"}
+        del ref, xr
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["gpu_eager_baseline"] = {"error": str(ex)[:300]}
+    return out
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra objects (train_ddp, a_series, detection, gpu_eager_baseline)")
     ap.add_argument("--model", default=MODEL, help="recnext_m0..m5 / recnext_a0..a5 (default: the metric's recnext_m3)")
     ap.add_argument("--train", action="store_true",
                     help="BASELINE.json configs[2]: training step (fwd + bwd + AdamW, bf16 autocast, DDP over NCCL when launched with torchrun) "
@@ -323,7 +472,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total, launches = timed(step_device, args.steps, instrument=True)
+    ms_total, _ = timed(step_device, args.steps)                    # the metric: no per-launch instrumentation in the timed region
+    n_inst = min(args.steps, 5)
+    ms_inst, launches = timed(step_device, n_inst, instrument=True)  # second pass: CUDA events around every launch of this repo's kernels
     # e2e: the repo's host-side inference loop (recnext_b200.infer.PipelinedInference): every step copies its batch from pinned
     # host memory and its logits back; the copy of batch i+1 overlaps the compute of batch i (separate copy stream)
     from recnext_b200.infer import PipelinedInference
@@ -364,20 +515,20 @@ def main():
     per_shape, dom = [], {"bytes": 0, "ms": 0.0, "n": 0}
     for shape, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
         if isinstance(shape[0], str):   # RecAttn2d pieces: ("down" | "up", B, C, H, W)
-            kern = {"ffn": "recnext_ffn_kernel", "dwdown": "recnext_dwdown_kernel"}.get(shape[0], "recconv_mfwd_kernel/" + shape[0])
+            kern = {"ffn": "recnext_ffn_tc_kernel", "dwdown": "recnext_dwdown_kernel"}.get(shape[0], "recconv_mfwd_kernel/" + shape[0])
         else:
             level = {56: 4, 28: 3, 14: 2, 7: 1}.get(shape[2], 0) if RES == 224 else None
             desc = RC.plan_describe(shape, 5, level, "bilinear", torch.bfloat16, False, False) if level is not None else ""
             kern = "recconv_mfwd_static_kernel" if "compile-time" in desc else ("recconv_mfwd_kernel" if "tensor-core" in desc else "recconv_wfwd_kernel")
         gbs = g["bytes"] / (g["ms"] * 1e-3) * 1e-9 if g["ms"] > 0 else 0.0
-        per_shape.append({"shape": list(shape), "kernel": kern, "launches_per_step": g["n"] / max(args.steps, 1),
+        per_shape.append({"shape": list(shape), "kernel": kern, "launches_per_step": g["n"] / max(n_inst, 1),
                           "avg_launch_ms": round(g["ms"] / g["n"], 5), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
         if kern.startswith("recconv_mfwd") or ("_a" in MODEL and kern.startswith("recconv_mfwd_kernel/")):
             dom["bytes"] += g["bytes"]; dom["ms"] += g["ms"]; dom["n"] += g["n"]
     if dom["n"] == 0:
         dom = {"bytes": sum(r["bytes"] for r in launches), "ms": sum(r["ms"] for r in launches), "n": len(launches)}
     kern_all_ms = sum(rec["ms"] for rec in launches)
-    n_launch = len(launches)
+    n_launch = int(round(len(launches) / max(n_inst, 1) * args.steps))   # launches of this repo's kernels in the K timed steps (counted in the instrumented pass)
     achieved = dom["bytes"] / (dom["ms"] * 1e-3) * 1e-9 if dom["ms"] > 0 else 0.0
     traffic = None
     try:
@@ -391,7 +542,8 @@ def main():
                   % (("", "RecAttn2d down / up-add-conv", dom["n"]) if "_a" in MODEL else ("_static", "RecConv", dom["n"])),
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
         "peak_source": peak_src, "bytes_per_launch": dom["bytes"] / max(dom["n"], 1), "avg_launch_ms": dom["ms"] / max(dom["n"], 1),
-        "share_of_step": round(dom["ms"] / ms_total, 4), "all_custom_kernels_share_of_step": round(kern_all_ms / ms_total, 4),
+        "share_of_step": round(dom["ms"] / ms_inst, 4), "all_custom_kernels_share_of_step": round(kern_all_ms / ms_inst, 4),
+        "measured_in": f"a second pass of {n_inst} steps with an event pair around every launch (the timed `value` pass carries no instrumentation)",
         "per_shape": per_shape,
         "note": "algorithmic bytes 2*N*e per launch (SURVEY 8d), CUDA events on the launching stream around every launch of the "
                 "timed steps.  The block is not HBM bound on B200: ~48 MAC per 4 bytes of bf16 traffic; the stencils run on the "
@@ -413,12 +565,14 @@ def main():
             tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md)"
         tf = fl / (fms * 1e-3) * 1e-12
         gbs = sum(r["bytes"] for r in ffn) / (fms * 1e-3) * 1e-9
-        roofline_ffn = {"bound": "tensor", "kernel": "recnext::recnext_ffn_kernel / recnext_ffn_staged_kernel<bf16> (fused channel mixer; %d launches)" % len(ffn),
+        roofline_ffn = {"bound": "tensor", "kernel": "recnext::recnext_ffn_tc_kernel<bf16> (fused channel mixer on tcgen05 / TMEM / TMA; %d launches)" % len(ffn),
                         "achieved": round(tf, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(tf / tpeak, 4), "peak_source": tsrc,
                         "hbm_gbs_of_3Ne": round(gbs, 1), "hbm_frac": round(gbs / peak, 4), "avg_launch_ms": fms / len(ffn),
-                        "share_of_step": round(fms / ms_total, 4),
-                        "note": "HMMA (mma.sync) kernel: bound by shared-memory operand traffic and pipeline fill at the wide stages, by the GELU's "
-                                "FP32 work at the narrow ones (DESIGN.md 3.3); listed because it is the largest kernel of the step by time"}
+                        "share_of_step": round(fms / ms_inst, 4),
+                        "note": "tcgen05.mma kernel (TMEM accumulators, TMA-streamed weight tiles): the narrow stages are bound by HBM and by the "
+                                "epilogue warps' instruction issue (GELU), the wide ones by the latency of the weight stream from L2 (DESIGN.md 3.3)"}
+
+    extras = {} if args.no_extras else run_extras(args, rank, world, dev, peak)
 
     if rank != 0:
         D.finalize()
@@ -442,10 +596,14 @@ def main():
         out["roofline_channel_mixer"] = roofline_ffn
     if not args.no_micro and "_a" not in MODEL:
         out["recconv_fwd_bwd"] = recconv_microbench(torch, R, peak)
+    out.update(extras)
     if not args.no_cpu_baseline:
-        rate, ms, threads = cpu_reference_rate(steps=3, warmup=1, batch=16)
-        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"16 images/step x 3 steps of the same model (fp32, eval, BN folded, PyTorch CPU eager, {threads} threads)"}
+        rate, ms, threads, kind = cpu_reference_rate(steps=3, warmup=1, batch=32)
+        m0_rate, m0_ms, _, _ = cpu_reference_rate(5, 2, 1, "recnext_m0")
+        what = "UNMODIFIED reference code (oracle/_ref)" if kind == "reference" else "restatement oracle/torch_ref.py"
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": f"32 images/step x 3 steps of the same model (fp32, eval, BN folded, PyTorch CPU eager, {threads} threads; {what})",
+                               "configs0_m0_batch1_fp32": {"images_per_s": m0_rate, "ms_per_image": m0_ms}}
     print(json.dumps(out), flush=True)
     D.finalize()
 

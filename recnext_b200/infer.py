@@ -15,8 +15,9 @@ import torch
 class PipelinedInference:
     """``for logits_host in PipelinedInference(model, autocast_dtype).run(host_batches): ...``
 
-    ``host_batches`` yields pinned CPU tensors of one fixed shape/dtype; every result is written to one of two pinned
-    host buffers, valid until the next-but-one ``next()`` (the iterator hands out buffer i while buffer i+1 is filled)."""
+    ``host_batches`` yields pinned CPU tensors of one fixed shape/dtype; every result is written to one of THREE pinned
+    host buffers used in rotation, so a yielded tensor stays valid until the next-but-one ``next()`` (while result i is in
+    the consumer's hands, result i+1 is being copied out and result i+2 goes to the third buffer)."""
 
     def __init__(self, model: torch.nn.Module, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, device: Optional[torch.device] = None):
         self.model = model.eval()
@@ -24,12 +25,15 @@ class PipelinedInference:
         self.device = device or next(model.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.device)
         self._xin = [None, None]
-        self._yout = [None, None]
+        self._yout = [None, None, None]
 
     def _stage(self, i: int, xh: torch.Tensor) -> torch.cuda.Event:
         """copy host batch -> device staging buffer i on the copy stream; returns the event that marks its arrival"""
         if self._xin[i] is None or self._xin[i].shape != xh.shape or self._xin[i].dtype != xh.dtype:
+            # a fresh block from the caching allocator may have just been freed by a kernel that is still queued on the main stream:
+            # the copy stream must not write it before the main stream has drained to this point
             self._xin[i] = torch.empty(xh.shape, dtype=xh.dtype, device=self.device)
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
             self._xin[i].copy_(xh, non_blocking=True)
             ev = torch.cuda.Event()
@@ -63,15 +67,16 @@ class PipelinedInference:
                 if consumed[cur ^ 1] is not None:
                     self.copy_stream.wait_event(consumed[cur ^ 1])
                 arrived = self._stage(cur ^ 1, nxt)
-            if self._yout[cur] is None or self._yout[cur].shape != y.shape or self._yout[cur].dtype != y.dtype:
-                self._yout[cur] = torch.empty(y.shape, dtype=y.dtype).pin_memory()
-            self._yout[cur].copy_(y, non_blocking=True)      # D2H on the main stream, behind the compute of this batch
+            yo = i % 3
+            if self._yout[yo] is None or self._yout[yo].shape != y.shape or self._yout[yo].dtype != y.dtype:
+                self._yout[yo] = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+            self._yout[yo].copy_(y, non_blocking=True)       # D2H on the main stream, behind the compute of this batch
             done = torch.cuda.Event()
             done.record(main)
             if pending is not None:
                 pending[1].synchronize()
                 yield pending[0]
-            pending = (self._yout[cur], done)
+            pending = (self._yout[yo], done)
             i += 1
         if pending is not None:
             pending[1].synchronize()

@@ -12,19 +12,18 @@ What runs where:
     ``recattn_down_forward`` / ``recattn_up_forward`` (include/recnext_b200.h), BatchNorm folded into (w, b);
   * the linear attention in between: its contraction chain (elu + 1, k v^T, mean(k), q^T kv / (q^T mean(k) + 1e-6), + pe;
     model/recattn.py:21-28, 44-51) is one more kernel (``recnext_linattn_forward``); its two ConvNorms (grouped 1x1 ``qk``,
-    depthwise 3x3 ``pe``) stay library convs.  Outside eval mode / 16-bit CUDA the reference's op chain runs as written.
-Inference only for now (16-bit CUDA activations, eval mode): training through the custom kernels needs their
-backward, which is not built yet, so ``forward`` raises in training mode instead of silently falling back.
+    depthwise 3x3 ``pe``) stay library convs.
+Inference only (CUDA activations, eval mode; the two RecAttn2d pieces 16-bit): training through the custom kernels needs
+their backward, which is not built, so ``forward`` raises in training mode, on CPU tensors and for head sizes the kernel does
+not have — there is no PyTorch fallback anywhere in this file (the eager restatement lives in oracle/torch_ref.py, for tests).
 """
 from __future__ import annotations
 
 import ctypes
-import os
 from typing import Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _native as N
 from . import recconv as _rc
@@ -163,38 +162,13 @@ def linattn_forward(qk: torch.Tensor, v: torch.Tensor, pe: Optional[torch.Tensor
 LINATTN_HEAD_DIMS = (4, 8, 16, 20, 24, 28, 32, 40)   # 20..40: the RecNeXt-A models; 4, 8, 16: small test models
 
 
-def _linattn_eligible(mod: nn.Module, x: torch.Tensor) -> bool:
-    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
-    return (not mod.training and x.is_cuda and dt in _DTYPES and mod.head_dim in LINATTN_HEAD_DIMS
-            and os.environ.get("RECNEXT_LINATTN", "1") != "0" and not torch.jit.is_tracing())
-
-
-class LinearAttention1(nn.Module):
-    """model/recattn.py:8-28 — kv formulation, O(n d^2)"""
-
-    def __init__(self, dim, num_heads):
-        super().__init__()
-        self.num_heads = num_heads
-        self.head_dim = dim // num_heads
-        self.qk = ConvNorm(dim, dim * 2, kernel_size=1, groups=2)
-        self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim)
-
-    def forward(self, x):
-        if _linattn_eligible(self, x):   # the whole contraction chain as one kernel; the two ConvNorms stay library convs
-            return linattn_forward(self.qk(x), x, self.pe(x), self.num_heads)
-        b, c, h, w = x.shape
-        n = h * w
-        s = n ** -0.5
-        qk = F.elu(self.qk(x)) + 1.0
-        (q, k), v = qk.view(b, 2, self.num_heads, self.head_dim, n).unbind(dim=1), x
-        q_t = q.transpose(-1, -2)
-        kv = (k * s) @ (v.view(b, self.num_heads, self.head_dim, n).transpose(-1, -2) * s)
-        x = q_t @ kv / (q_t @ k.mean(dim=-1, keepdim=True) + 1e-6)
-        return x.transpose(-1, -2).reshape(b, c, h, w) + self.pe(v)
-
-
-class LinearAttention2(nn.Module):
-    """model/recattn.py:31-51 — quadratic formulation, used where n is tiny (stage 3)"""
+class _LinearAttention(nn.Module):
+    """The linear attention of the A-series token mixer.  The reference spells it twice — LinearAttention1 (model/recattn.py:8-28, the
+    d x d ``kv`` form, stages 0-2) and LinearAttention2 (:31-51, the n x n form, stage 3, n = 16) — and checks that the two agree
+    (lsnet/model/recattn.py:480-501); both are served by ONE kernel that always takes the d x d route (``recnext_linattn_forward``):
+    q, k = elu(qk(x)) + 1;  out = q^T (k v^T / n) / (q^T mean(k) + 1e-6) + pe(x).  Sub-module names (``qk``, ``pe``) and therefore the
+    ``state_dict`` are the reference's.  Inference only: there is no backward and, deliberately, no PyTorch fallback — anything the
+    kernel does not serve raises."""
 
     def __init__(self, dim, num_heads):
         super().__init__()
@@ -204,17 +178,21 @@ class LinearAttention2(nn.Module):
         self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim)
 
     def forward(self, x):
-        if _linattn_eligible(self, x):   # same function as LinearAttention1 (model/recattn.py:56-57): same kernel
-            return linattn_forward(self.qk(x), x, self.pe(x), self.num_heads)
-        b, c, h, w = x.shape
-        n = h * w
-        s = n ** -0.5
-        qk = F.elu(self.qk(x)) + 1.0
-        (q, k), v = qk.view(b, 2, self.num_heads, self.head_dim, n).unbind(dim=1), x
-        qk = q.transpose(-1, -2) @ k
-        qk = qk / (qk.mean(dim=-1, keepdim=True) + 1e-6)
-        x = (qk * s) @ (v.view(b, self.num_heads, self.head_dim, n).transpose(-1, -2) * s)
-        return x.transpose(-1, -2).reshape(b, c, h, w) + self.pe(v)
+        if self.training:
+            raise RuntimeError("recnext_b200 linear attention: the sm_100a kernel has no backward — call .eval(); there is deliberately no PyTorch fallback")
+        if not x.is_cuda:
+            raise RuntimeError("recnext_b200 linear attention runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.head_dim not in LINATTN_HEAD_DIMS:
+            raise RuntimeError(f"recnext_b200 linear attention: head_dim {self.head_dim} is not built (have {LINATTN_HEAD_DIMS})")
+        return linattn_forward(self.qk(x), x, self.pe(x), self.num_heads)
+
+
+class LinearAttention1(_LinearAttention):
+    """model/recattn.py:8-28"""
+
+
+class LinearAttention2(_LinearAttention):
+    """model/recattn.py:31-51 (same function, model/recattn.py:56-57)"""
 
 
 class RecAttn2d(nn.Module):

