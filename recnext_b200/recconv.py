@@ -198,7 +198,13 @@ class RecConv2d(nn.Module):
         # the kernels work on NCHW planes; a channels_last input is transposed once and the result is handed back in
         # the caller's memory format (what nn.Conv2d does), so a channels_last model keeps its 1x1 convs transpose-free
         channels_last = x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
-        y = _RecConvFn.apply(x, self.kernel_size, self.level, self.mode, len(biases), *weights, *biases)
+        if x.is_cuda:
+            # the registered operator (recnext_b200/ops.py): one node for jit.trace / torch.compile, same C-ABI call in eager
+            from . import ops as _ops  # noqa: F401  (registers torch.ops.recnext.*)
+
+            y = torch.ops.recnext.recconv(x, list(weights), list(biases), self.kernel_size, self.level, self.mode)
+        else:
+            y = _RecConvFn.apply(x, self.kernel_size, self.level, self.mode, len(biases), *weights, *biases)   # raises: no CPU path
         return y.contiguous(memory_format=torch.channels_last) if channels_last else y
 
     def extra_repr(self):
