@@ -440,6 +440,8 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                 }
                 tc::mbar_wait(bar(D2_FULL + db), ((uint32_t)t / nD2) & 1u);
                 tc::fence_after_sync();
+                group_sync();   // (the mbarrier chain already orders this group's H stores before the staging stores below; the barrier
+                                //  states it in a form compute-sanitizer's racecheck can follow)
                 if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 3);
                 for (int ct = 0; ct < nCT; ++ct) {
                     if (ct > 0) {

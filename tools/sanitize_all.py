@@ -11,13 +11,18 @@ for (B, C, H, W, L, mode) in [(2, 8, 56, 56, 4, "bilinear"), (2, 8, 28, 28, 3, "
     x = torch.randn(B, C, H, W, device=dev).bfloat16()
     ws = [torch.empty(C, 1, 5, 5, device=dev).uniform_(-0.2, 0.2) for _ in range(L + 2)]
     y = R.recconv_forward(x, ws, None, 5, L, mode)
-    if H <= 56:
-        gx, gw, _ = R.recconv_backward(x, torch.randn_like(x), ws, None, 5, L, mode)
+    gx, gw, _ = R.recconv_backward(x, torch.randn_like(x), ws, None, 5, L, mode)   # tensor-core / FMA / streamed backward by shape
     print("recconv", (B, C, H, W, L, mode), float(y.float().abs().mean()))
 x = torch.randn(2, 8, 28, 28, device=dev).bfloat16(); w = torch.randn(8, 1, 5, 5, device=dev) * 0.1; b = torch.randn(8, device=dev) * 0.1
 low = R.recattn_down_forward(x, w, b); y = R.recattn_up_forward(x, low, w, b, "nearest"); y2 = R.recattn_up_forward(x, low, w, b, "bilinear")
 print("recattn", float(y.float().abs().mean()), float(y2.float().abs().mean()))
-for (B, C, H) in [(2, 64, 28), (2, 128, 14), (2, 256, 14), (1, 320, 14), (1, 48, 10)]:
+xf = torch.randn(1, 4, 25, 21, device=dev)   # fp32: FMA kernels; forced streamed path
+wf = [torch.empty(4, 1, 5, 5, device=dev).uniform_(-0.2, 0.2) for _ in range(4)]
+os.environ["RECNEXT_PATH"] = "stream"
+R.recconv_forward(xf, wf, None, 5, 2, "bilinear"); R.recconv_backward(xf, torch.randn_like(xf), wf, None, 5, 2, "nearest")
+del os.environ["RECNEXT_PATH"]
+print("streamed ok")
+for (B, C, H) in [(2, 64, 28), (2, 128, 14), (2, 256, 14), (1, 320, 14), (1, 48, 10), (2, 512, 7), (3, 40, 9)]:
     hid = 2 * C
     yy = torch.randn(B, C, H, H, device=dev).bfloat16(); xx = torch.randn_like(yy)
     o = ffn_forward(yy, xx, torch.randn(hid, C, device=dev).bfloat16() * 0.1, torch.randn(hid, device=dev), torch.randn(C, hid, device=dev).bfloat16() * 0.1, torch.randn(C, device=dev))
