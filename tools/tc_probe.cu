@@ -183,6 +183,27 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int N, int nrep, int mode,
             }
             if (lane == 0) res[warp * 4 + 3] = n + (v.x & 1);
         }
+    } else if (mode == 8 || mode == 9 || mode == 10) {
+        // issue-side cost of the hand-offs around a group of 4 MMAs (N columns): mode 8: 4 MMAs + tcgen05.commit per group; mode 9: the same
+        // plus a try_wait on an already completed mbarrier and a tcgen05.fence::after_thread_sync; mode 10: 4 MMAs only (one commit at the end)
+        if (uwarp == 0) {
+            uint32_t elected = 0;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+            if (elected) tc::mbar_arrive(bar1);   // bar1 completes its phase 0: try_wait(bar1, 0) succeeds immediately from now on
+            __syncwarp();
+            t0 = clock64();
+            for (int i = 0; i < nrep; ++i) {
+                if (mode == 9) { tc::mbar_wait(bar1, 0); tc::fence_after_sync(); }
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t a_i = tc::sdesc_advance(ad, (uint32_t)j * 4096u);
+                    if (elected) tc::mma_ss(tbase + (i & 1) * N, a_i, bd, idesc, 1);
+                }
+                if (mode != 10 && elected) tc::mma_commit(bar0);
+            }
+            if (mode == 10 && elected) tc::mma_commit(bar0);
+            t1 = clock64();
+            if (lane == 0) { res[0] = t1 - t0; res[1] = t1 - t0; res[2] = 1; }
+        }
     } else if (mode == 3) {
         if (tid == 0) {
             t0 = clock64();
@@ -323,7 +344,8 @@ int main() {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("[%s] KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(4); }
         long long r[16]; CK(cudaMemcpy(r, dres, sizeof r, cudaMemcpyDeviceToHost));
-        if (mode >= 5) printf("[time %s] N=%d nrep=%d total=%lld cyc (%.1f / MMA) ok=%lld  neighbour 16-byte accesses per warp: %lld %lld %lld (%.1f B/cyc)\n", name, N, nrep, r[1], (double)r[1] / nrep, r[2], r[7], r[11], r[15], 16.0 * 32 * (r[7] + r[11] + r[15]) / (double)r[1]);
+        if (mode >= 8) printf("[time %s] N=%d groups=%d issue time %lld cyc (%.1f per group of 4 MMAs; math floor %.0f)\n", name, N, nrep, r[0], (double)r[0] / nrep, 4.0 * (N >= 128 ? N / 2.0 : (N == 64 ? 48.0 : 39.0)));
+        else if (mode >= 5) printf("[time %s] N=%d nrep=%d total=%lld cyc (%.1f / MMA) ok=%lld  neighbour 16-byte accesses per warp: %lld %lld %lld (%.1f B/cyc)\n", name, N, nrep, r[1], (double)r[1] / nrep, r[2], r[7], r[11], r[15], 16.0 * 32 * (r[7] + r[11] + r[15]) / (double)r[1]);
         else if (mode == 0 || mode == 3) printf("[time %s] N=%d nrep=%d issue=%lld cyc total=%lld cyc (%.1f / MMA) ok=%lld\n", name, N, nrep, r[0], r[1] ? r[1] : r[0], (double)(r[1] ? r[1] : r[0]) / nrep, r[2]);
         else if (mode == 1) printf("[time %s] N=%d nrep=%d x2 issuers: w0 total=%lld w1 total=%lld (%.1f cyc / MMA overall) ok=%lld,%lld\n", name, N, nrep, r[1], r[5], (double)(r[1] > r[5] ? r[1] : r[5]) / (2.0 * nrep), r[2], r[6]);
         else printf("[time %s] cols=%d nrep=%d per-warp cycles %lld %lld %lld %lld -> %.1f B/cyc/SM\n", name, N, nrep, r[0], r[4], r[8], r[12], 4.0 * 32 * N * 4 * nrep / (double)r[0]);
@@ -342,6 +364,10 @@ int main() {
         timeit("mma_n128_mnB_plus_lds", 128, 1024, 7, 128, 2048);
         timeit("mma_n256_mnB", 256, 512, 5, 128, 2048);
         timeit("mma_n256_mnB_plus_sts", 256, 512, 6, 128, 2048);
+        timeit("4mma_n128_only", 128, 256, 10, 128, 2048);
+        timeit("4mma_n128_commit", 128, 256, 8, 128, 2048);
+        timeit("4mma_n128_wait_fence_commit", 128, 256, 9, 128, 2048);
+        timeit("4mma_n64_commit", 64, 256, 8, 128, 2048);
         timeit("tmem_ld", 512, 64, 2, 128, 2048);
         timeit("tmem_ld_pipelined4", 512, 64, 4, 128, 2048);
         timeit("roundtrip_n16", 16, 256, 3, 128, 2048);
