@@ -34,19 +34,28 @@ namespace {
 
 constexpr int kRing = 8;             // weight ring slots at most (the plan takes as many as fit: 4 .. 8)
 constexpr int kTileBytes = 16384;    // 128 rows x 64 K x 2 bytes
-constexpr int kEpiWarps = 8, kLoadWarps = 4;
-constexpr int kThreads = 32 * (kEpiWarps + 2 + kLoadWarps);
+constexpr int kEpiWarps = 8, kLoadWarps = 2, kWriteWarps = 4;
+constexpr int kThreads = 32 * (kEpiWarps + 2 + kLoadWarps + kWriteWarps);   // 512
+constexpr int kLoad0 = 32 * (kEpiWarps + 2);                                // first loader thread
 constexpr uint32_t kSboH = 128 * 16 + 16;   // H: one 8-pixel chunk of all 128 hidden rows + 16 bytes (conflict-free chunk stores)
 
 template <typename T> struct Cvt;
 template <> struct Cvt<__nv_bfloat16> {
     static __device__ __forceinline__ uint32_t pack(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
     static __device__ __forceinline__ float2 unpack(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {   // one correctly rounded 16-bit add per element (HADD2.BF16)
+        __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
     static constexpr int fmt = 1;
 };
 template <> struct Cvt<__half> {
     static __device__ __forceinline__ uint32_t pack(float lo, float hi) { __half2 v = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
     static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {
+        __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&r);
+    }
     static constexpr int fmt = 0;
 };
 
@@ -86,6 +95,32 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, bool va
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid ? 8 : 0) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// size-parametrised forms: `bytes` = 0 zero-fills (src must still be a valid address)
+__device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8z(uint32_t dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+// predicated global accesses without a branch (a helper warp runs alone on its scheduler: every instruction costs its full latency)
+__device__ __forceinline__ uint2 ldg64p(const void* p, bool v) {
+    uint2 r;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t@q ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
+                 : "=r"(r.x), "=r"(r.y) : "l"(p), "r"((int)v));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg128p(const void* p, bool v) {
+    uint4 r;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t@q ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "r"((int)v));
+    return r;
+}
+__device__ __forceinline__ void stg64p(void* p, uint32_t a, uint32_t b, bool v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.v2.b32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(a), "r"(b), "r"((int)v) : "memory");
+}
+__device__ __forceinline__ void stg128p(void* p, uint4 w, bool v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w), "r"((int)v) : "memory");
+}
 
 // Position of a pixel of the flattened batch: image b, pixel i inside the image.  Tiles walk forward through the pixels, so the
 // (slow) integer division happens once per tile and thread; everything else is increments.
@@ -104,58 +139,53 @@ __device__ __forceinline__ Pix pix_add(Pix a, int n, int HW) {
     return a;
 }
 
-// 8 consecutive pixels starting at `px` of channel row `ch`; pixels of images >= B read as zero / are not written.
-// VEC = 8: HW % 8 == 0, one 16-byte access; VEC = 4: HW % 4 == 0, two 8-byte accesses; VEC = 1: element-wise.
-template <typename T, int VEC>
-__device__ __forceinline__ uint4 load8(const T* __restrict__ base, Pix px, int B, int C, int HW, int ch) {
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (VEC == 8) {
-        if (px.b < B) v = *reinterpret_cast<const uint4*>(base + (((long)px.b * C + ch) * (long)HW + px.i));
-    } else if (VEC == 4) {
-        uint2 h[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (px.b < B) h[u] = *reinterpret_cast<const uint2*>(base + (((long)px.b * C + ch) * (long)HW + px.i));
-            px = pix_add(px, 4, HW);
-        }
-        v = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
-    } else {
-        unsigned short e[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            e[u] = 0;
-            if (px.b < B) e[u] = *reinterpret_cast<const unsigned short*>(base + (((long)px.b * C + ch) * (long)HW + px.i));
-            px = pix_add(px, 1, HW);
-        }
-        v = make_uint4(e[0] | ((uint32_t)e[1] << 16), e[2] | ((uint32_t)e[3] << 16), e[4] | ((uint32_t)e[5] << 16), e[6] | ((uint32_t)e[7] << 16));
+// Where the 8-pixel chunk at tile-space position `px` lives: element offsets (for channel 0 of its image) of its aligned pieces.
+//   VEC = 8: one 16-byte piece.   VEC = 4: two 8-byte pieces (HW % 8 == 4: the second may lie in the next image).
+//   VEC = 1: images are padded to a multiple of 8 columns in TILE SPACE (FfnTcPlan::HWp), so a chunk is `nv` <= 8 consecutive
+//            16-bit elements of one row (nv < 8 only for the last chunk of an image); the padding columns compute garbage that is
+//            never stored (columns of a GEMM do not mix).
+template <int VEC>
+struct ChunkAddr {
+    long o0, o1;
+    bool v0, v1;
+    int nv;
+    __device__ __forceinline__ ChunkAddr(Pix px, int B, int C, int HW) {
+        o0 = ((long)px.b * C) * (long)HW + px.i; v0 = px.b < B;
+        if (VEC == 4) {
+            const Pix q = pix_add(px, 4, HW);
+            o1 = ((long)q.b * C) * (long)HW + q.i; v1 = q.b < B;
+        } else { o1 = o0; v1 = false; }
+        nv = (VEC == 1 && v0) ? max(0, min(8, HW - px.i)) : 0;
     }
-    return v;
-}
-template <typename T, int VEC>
-__device__ __forceinline__ void store8(T* __restrict__ base, Pix px, int B, int C, int HW, int ch, uint4 v) {
-    if (VEC == 8) {
-        if (px.b < B) *reinterpret_cast<uint4*>(base + (((long)px.b * C + ch) * (long)HW + px.i)) = v;
-    } else if (VEC == 4) {
-        const uint2 h[2] = {make_uint2(v.x, v.y), make_uint2(v.z, v.w)};
+};
+// the element-wise forms (VEC = 1): `row` points at the chunk's first element of one channel row
+__device__ __forceinline__ uint4 load8e(const unsigned short* __restrict__ row, int nv) {
+    uint32_t e[8];
+    if (nv == 8) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (px.b < B) *reinterpret_cast<uint2*>(base + (((long)px.b * C + ch) * (long)HW + px.i)) = h[u];
-            px = pix_add(px, 4, HW);
-        }
+        for (int u = 0; u < 8; ++u) e[u] = __ldg(row + u);
     } else {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (px.b < B)
-                *reinterpret_cast<unsigned short*>(base + (((long)px.b * C + ch) * (long)HW + px.i)) = (unsigned short)((w[u >> 1] >> (16 * (u & 1))) & 0xffffu);
-            px = pix_add(px, 1, HW);
-        }
+        for (int u = 0; u < 8; ++u) e[u] = u < nv ? (uint32_t)__ldg(row + u) : 0u;
+    }
+    return make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+}
+__device__ __forceinline__ void store8e(unsigned short* __restrict__ row, int nv, uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (nv == 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) row[u] = (unsigned short)((w[u >> 1] >> (16 * (u & 1))) & 0xffffu);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (u < nv) row[u] = (unsigned short)((w[u >> 1] >> (16 * (u & 1))) & 0xffffu);
     }
 }
 
-constexpr int kMaxY = 4;   // activation tile buffers at most
+constexpr int kMaxY = 12;  // activation tile buffers (at most 4) -- or, with ONE buffer, its 64-channel slabs (C <= 768), each with its own barriers
 enum Bar { W_FULL = 0, W_EMPTY = kRing, Y_FULL = 2 * kRing, Y_EMPTY = Y_FULL + kMaxY, D1_FULL = Y_EMPTY + kMaxY, H_FULL = D1_FULL + 2,
-           H_EMPTY = H_FULL + 2, D2_FULL = H_EMPTY + 2, D2_EMPTY = D2_FULL + 2, NUM_BARS = D2_EMPTY + 2 };
+           H_EMPTY = H_FULL + 2, D2_FULL = H_EMPTY + 2, D2_EMPTY = D2_FULL + 2, OUT_FULL = D2_EMPTY + 2, OUT_EMPTY = OUT_FULL + 2,
+           NUM_BARS = OUT_EMPTY + 2 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -198,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(bar(D1_FULL + i), 1); tc::mbar_init(bar(H_FULL + i), 4); tc::mbar_init(bar(H_EMPTY + i), 1);
             tc::mbar_init(bar(D2_FULL + i), 1); tc::mbar_init(bar(D2_EMPTY + i), 4);
+            tc::mbar_init(bar(OUT_FULL + i), 4); tc::mbar_init(bar(OUT_EMPTY + i), kWriteWarps);
         }
         tc::mbar_init_fence();
     }
@@ -223,159 +254,319 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
     const int RS = p.RS, nY = p.nY, nD2 = p.nD2;
     const uint32_t w1_step = (uint32_t)(128 * 2) * (uint32_t)p.CP, w2_step = (uint32_t)(2 * nCT) * kTileBytes;
 
+    // Order of the weight stream (producer and MMA issuer walk it identically): per chunk g the W1 tiles of chunk g, then the W2 tiles
+    // of chunk g - 1 -- except at a tile border when there is ONE activation buffer: then GEMM2 of the previous tile's last chunk goes
+    // first, so that tile's output leaves (and its accumulator frees) while the next activation tile is still loading.
+    const bool border_swap = (p.nY == 1);
     if (warp == 8) {
         // ================= weight producer =================
-        // stream order = the MMA warp's: W1 tiles of chunk g, then the W2 tiles of chunk g - 1.  In a cluster every CTA fetches
-        // 1/CS of each tile and multicasts it to all of them: L2 is read once per cluster.
-        uint32_t use = 0;
+        // In a cluster every CTA fetches 1/CS of each tile and multicasts it to all of them: L2 is read once per cluster.
         const bool leader = elect_one();
         const uint8_t* w2base = wpk + (size_t)nH * w1_step;
+        const uint32_t wfull0 = bar(W_FULL), wempty0 = bar(W_EMPTY), ring0 = sb + p.offW;
+        const uint32_t last_bytes = (uint32_t)(128 * 2) * (uint32_t)p.kwLast;
+        uint32_t slot = 0, phase = 1;    // (phase of the EMPTY barrier a fresh slot passes immediately)
+        auto put = [&](const uint8_t* src, uint32_t bytes) {
+            tc::mbar_wait(wempty0 + 8u * slot, phase);
+            if (leader) {
+                if (p.dbg & 1) tc::mbar_arrive(wfull0 + 8u * slot);   // timing experiment: no weight traffic (results are garbage)
+                else {
+                    tc::mbar_expect_tx(wfull0 + 8u * slot, bytes);
+                    if (CS == 1) tc::bulk_g2s(ring0 + slot * kTileBytes, src, bytes, wfull0 + 8u * slot);
+                    else {
+                        const uint32_t part = bytes / (uint32_t)CS;
+                        bulk_g2s_mcast(ring0 + slot * kTileBytes + crank * part, src + crank * part, part, wfull0 + 8u * slot, cmask);
+                    }
+                }
+            }
+            if (++slot == (uint32_t)RS) { slot = 0; phase ^= 1u; }
+        };
         int s = 0;
         for (int g = 0; g <= G; ++g) {
             const int s_prev = s == 0 ? nH - 1 : s - 1;
-            const int n1 = g < G ? nK1 : 0, n2 = g >= 1 ? 2 * nCT : 0;
             const uint8_t* src1 = wpk + (size_t)s * w1_step;
             const uint8_t* src2 = w2base + (size_t)s_prev * w2_step;
-            for (int t = 0; t < n1 + n2; ++t) {
-                const uint32_t bytes = t < n1 ? (uint32_t)(128 * 2 * (t == nK1 - 1 ? p.kwLast : 64)) : (uint32_t)kTileBytes;
-                const uint8_t* src = t < n1 ? src1 + (size_t)t * kTileBytes : src2 + (size_t)(t - n1) * kTileBytes;
-                const uint32_t slot = use % RS;
-                tc::mbar_wait(bar(W_EMPTY + slot), ((use / RS) & 1u) ^ 1u);
-                if (leader) {
-                    if (p.dbg & 1) tc::mbar_arrive(bar(W_FULL + slot));   // timing experiment: no weight traffic (results are garbage)
-                    else {
-                        tc::mbar_expect_tx(bar(W_FULL + slot), bytes);
-                        if (CS == 1) tc::bulk_g2s(sb + p.offW + slot * kTileBytes, src, bytes, bar(W_FULL + slot));
-                        else {
-                            const uint32_t part = bytes / (uint32_t)CS;
-                            bulk_g2s_mcast(sb + p.offW + slot * kTileBytes + crank * part, src + crank * part, part, bar(W_FULL + slot), cmask);
-                        }
+            const bool second_first = border_swap && s == 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                if ((pass == 0) != second_first) {
+                    if (g < G) {
+                        for (int t = 0; t < nK1 - 1; ++t) put(src1 + (size_t)t * kTileBytes, kTileBytes);
+                        put(src1 + (size_t)(nK1 - 1) * kTileBytes, last_bytes);
                     }
+                } else if (g >= 1) {
+                    for (int t = 0; t < 2 * nCT; ++t) put(src2 + (size_t)t * kTileBytes, kTileBytes);
                 }
-                ++use;
             }
             if (++s == nH) s = 0;
         }
     } else if (warp == 9) {
         // ================= MMA issuer =================
+        // One warp, warp-uniform control flow, one elected lane issues.  The loop is the critical resource of the kernel for C >= 128
+        // (a hand-off costs the tensor pipe as much as the instructions between two tcgen05.mma take to issue), so ring positions,
+        // barrier phases and descriptors are carried incrementally: no divisions, nothing recomputed per slot.
         const bool leader = elect_one();
         const uint32_t idesc = tc::make_idesc(128, NT, Cvt<T>::fmt, 0, 1);
-        auto release_slot = [&](uint32_t slot) {
-            if (CS == 1) tc::mma_commit(bar(W_EMPTY + slot));
-            else mma_commit_mcast(bar(W_EMPTY + slot), cmask);
+        const uint32_t wfull0 = bar(W_FULL), wempty0 = bar(W_EMPTY);
+        const uint64_t a_ring = tc::make_sdesc(sb + p.offW, 2048, 128);
+        const uint64_t y_desc0 = tc::make_sdesc(sb + p.offY, 128, p.sboY);
+        const uint64_t h_desc0 = tc::make_sdesc(sb + p.offH, 128, kSboH);
+        const int last_steps = p.kwLast / 16;
+        uint32_t wslot = 0, wphase = 0;
+        // four (or `steps`) K steps of one ring slot: D (+)= A[slot] . B
+        long long acc_wait = 0, acc_issue = 0, acc_slots = 0;
+        const bool profiling = prof != nullptr && blockIdx.x == 0;
+        auto slot_mmas = [&](uint32_t d, uint64_t bd, bool fresh, int steps) {
+            long long c0 = 0, c1 = 0;
+            if (profiling) c0 = clock64();
+            tc::mbar_wait(wfull0 + 8u * wslot, wphase);
+            tc::fence_after_sync();
+            if (profiling) c1 = clock64();
+            const uint64_t ad = a_ring + (uint64_t)(wslot * (kTileBytes / 16));
+            if (steps == 4) {
+                if (leader) {
+                    tc::mma_ss(d, ad, bd, idesc, fresh ? 0u : 1u);
+                    tc::mma_ss(d, ad + 256, bd + 16, idesc, 1u);
+                    tc::mma_ss(d, ad + 512, bd + 32, idesc, 1u);
+                    tc::mma_ss(d, ad + 768, bd + 48, idesc, 1u);
+                }
+            } else {
+                for (int j = 0; j < steps; ++j)
+                    if (leader) tc::mma_ss(d, ad + (uint64_t)(256 * j), bd + (uint64_t)(16 * j), idesc, (fresh && j == 0) ? 0u : 1u);
+            }
+            if (leader) {
+                if (CS == 1) tc::mma_commit(wempty0 + 8u * wslot);
+                else mma_commit_mcast(wempty0 + 8u * wslot, cmask);
+            }
+            if (profiling) { const long long c2 = clock64(); acc_wait += c1 - c0; acc_issue += c2 - c1; ++acc_slots; }
+            if (++wslot == (uint32_t)RS) { wslot = 0; wphase ^= 1u; }
         };
-        uint32_t wuse = 0;
-        int s = 0, t = 0;            // chunk g = (tile t of this CTA, hidden chunk s)
-        int s2 = 0, t2 = 0;          // chunk g - 1
+        int s = 0;                                  // chunk g = (tile of this CTA, hidden chunk s)
+        uint32_t ybuf = 0, yphase = 0;              // activation buffer of chunk g's tile
+        int s2 = 0;                                 // chunk g - 1
+        uint32_t db = 0, dphase = 1;                // output accumulator of chunk g - 1's tile (EMPTY barrier: a fresh one passes)
+        const bool slabs = (nY == 1);                // one activation buffer, handed over in 64-channel slabs (barrier per slab)
+        auto y_acquire = [&](uint32_t bi) {
+            tc::mbar_wait(bar(Y_FULL) + 8u * bi, yphase);
+            tc::fence_proxy_async();   // the loaders' cp.async / st.shared writes -> the tensor core's async-proxy reads
+            tc::fence_after_sync();
+        };
+        auto gemm1 = [&](int g) {                   // D1[g & 1] = W1[s] . Y
+            if (s == 0 && !slabs) y_acquire(ybuf);
+            const uint32_t buf = (uint32_t)g & 1u;
+            const uint32_t d1 = tbase + buf * NT;
+            const uint64_t bd0 = y_desc0 + (uint64_t)(ybuf * (p.yBytes / 16));
+            stamp(0, 4 * g + 0);
+            for (int kc = 0; kc < nK1; ++kc) {
+                if (slabs && s == 0) y_acquire((uint32_t)kc);
+                slot_mmas(d1, bd0 + (uint64_t)(kc * 64), kc == 0, kc == nK1 - 1 ? last_steps : 4);
+                if (slabs && s == nH - 1 && leader) tc::mma_commit(bar(Y_EMPTY) + 8u * (uint32_t)kc);   // the next tile's slab may land
+            }
+            if (leader) {
+                tc::mma_commit(bar(D1_FULL) + 8u * buf);
+                if (s == nH - 1 && !slabs) tc::mma_commit(bar(Y_EMPTY) + 8u * ybuf);   // the loaders may fetch this buffer's next tile
+            }
+            stamp(0, 4 * g + 1);
+            if (++s == nH) {
+                s = 0;
+                if (slabs) yphase ^= 1u;
+                else if (++ybuf == (uint32_t)nY) { ybuf = 0; yphase ^= 1u; }
+            }
+        };
+        auto gemm2 = [&](int gg) {                  // D2 += W2[:, s2] . H[gg & 1]
+            const uint32_t buf = (uint32_t)gg & 1u;
+            tc::mbar_wait(bar(H_FULL) + 8u * buf, ((uint32_t)gg >> 1) & 1u);
+            if (s2 == 0) tc::mbar_wait(bar(D2_EMPTY) + 8u * db, dphase);   // that accumulator's previous tile has left TMEM
+            tc::fence_after_sync();
+            stamp(0, 4 * gg + 2);
+            const uint64_t hd = h_desc0 + (uint64_t)(buf * (p.hBytes / 16));
+            for (int ct = 0; ct < nCT; ++ct) {
+                const uint32_t d2 = tbase + 2 * NT + (db * nCT + ct) * NT;
+                slot_mmas(d2, hd, s2 == 0, 4);
+                slot_mmas(d2, hd + 64, false, 4);
+            }
+            if (leader) {
+                tc::mma_commit(bar(H_EMPTY) + 8u * buf);
+                if (s2 == nH - 1) tc::mma_commit(bar(D2_FULL) + 8u * db);
+            }
+            stamp(0, 4 * gg + 3);
+            if (++s2 == nH) {
+                s2 = 0;
+                if (++db == (uint32_t)nD2) { db = 0; dphase ^= 1u; }
+            }
+        };
+        const long long role0 = profiling ? clock64() : 0;
         for (int g = 0; g <= G; ++g) {
-            if (g < G) {   // GEMM1 of chunk g:  D1[g & 1] = W1[s] . Y[t]
-                const uint32_t ybuf = (uint32_t)t % nY;
-                if (s == 0) {
-                    tc::mbar_wait(bar(Y_FULL + ybuf), ((uint32_t)t / nY) & 1u);
-                    tc::fence_proxy_async();   // the loaders' cp.async / st.shared writes -> the tensor core's async-proxy reads
-                    tc::fence_after_sync();
-                }
-                const uint32_t ybase = sb + p.offY + ybuf * p.yBytes;
-                const uint32_t buf = (uint32_t)g & 1u;
-                const uint32_t d1 = tbase + buf * NT;
-                stamp(0, 4 * g + 0);
-                for (int kc = 0; kc < nK1; ++kc) {
-                    const uint32_t slot = wuse % RS;
-                    tc::mbar_wait(bar(W_FULL + slot), (wuse / RS) & 1u);
-                    tc::fence_after_sync();
-                    const int ksteps = (kc == nK1 - 1 ? p.kwLast : 64) / 16;
-                    const uint64_t ad = tc::make_sdesc(sb + p.offW + slot * kTileBytes, 2048, 128);
-                    const uint64_t bd = tc::make_sdesc(ybase + (uint32_t)(kc * 64) * 16u, 128, p.sboY);
-                    for (int j = 0; j < ksteps; ++j)
-                        if (leader) tc::mma_ss(d1, tc::sdesc_advance(ad, (uint32_t)j * 4096u), tc::sdesc_advance(bd, (uint32_t)j * 256u), idesc, (kc | j) != 0);
-                    if (leader) release_slot(slot);
-                    ++wuse;
-                }
-                if (leader) {
-                    tc::mma_commit(bar(D1_FULL + buf));
-                    if (s == nH - 1) tc::mma_commit(bar(Y_EMPTY + ybuf));   // the loaders may fetch this buffer's next tile
-                }
-                stamp(0, 4 * g + 1);
-                if (++s == nH) { s = 0; ++t; }
-            }
-            if (g >= 1) {   // GEMM2 of chunk g - 1:  D2[t2] += W2[:, s2] . H[(g - 1) & 1]
-                const uint32_t gg = (uint32_t)(g - 1), buf = gg & 1u;
-                const uint32_t db = (uint32_t)t2 % nD2;
-                tc::mbar_wait(bar(H_FULL + buf), (gg >> 1) & 1u);
-                if (s2 == 0) tc::mbar_wait(bar(D2_EMPTY + db), (((uint32_t)t2 / nD2) & 1u) ^ 1u);   // that accumulator's previous tile has left TMEM
-                tc::fence_after_sync();
-                stamp(0, 4 * (g - 1) + 2);
-                const uint32_t hbase = sb + p.offH + buf * p.hBytes;
-                for (int ct = 0; ct < nCT; ++ct) {
-                    const uint32_t d2 = tbase + 2 * NT + (db * nCT + ct) * NT;
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t slot = wuse % RS;
-                        tc::mbar_wait(bar(W_FULL + slot), (wuse / RS) & 1u);
-                        tc::fence_after_sync();
-                        const uint64_t ad = tc::make_sdesc(sb + p.offW + slot * kTileBytes, 2048, 128);
-                        const uint64_t bd = tc::make_sdesc(hbase + (uint32_t)(half * 64) * 16u, 128, kSboH);
-                        for (int j = 0; j < 4; ++j)
-                            if (leader) tc::mma_ss(d2, tc::sdesc_advance(ad, (uint32_t)j * 4096u), tc::sdesc_advance(bd, (uint32_t)j * 256u), idesc, !(s2 == 0 && half == 0 && j == 0));
-                        if (leader) release_slot(slot);
-                        ++wuse;
-                    }
-                }
-                if (leader) {
-                    tc::mma_commit(bar(H_EMPTY + buf));
-                    if (s2 == nH - 1) tc::mma_commit(bar(D2_FULL + db));
-                }
-                stamp(0, 4 * (g - 1) + 3);
-                if (++s2 == nH) { s2 = 0; ++t2; }
-            }
+            const bool second_first = border_swap && s == 0;
+            if (second_first && g >= 1) gemm2(g - 1);
+            if (g < G) gemm1(g);
+            if (!second_first && g >= 1) gemm2(g - 1);
         }
-    } else if (warp >= 10) {
+        if (profiling && lane == 0) { prof[500] = acc_wait; prof[501] = acc_issue; prof[502] = acc_slots; prof[503] = clock64() - role0; }
+    } else if (warp >= 10 && warp < 10 + kLoadWarps) {
         // ================= activation loaders =================
-        // Fully asynchronous: a thread issues the cp.async copies of its part of a tile and attaches an mbarrier arrival to them
-        // (no wait), then moves on to the next tile as soon as that buffer is free: up to nY tiles are in flight.
+        // Fully asynchronous: a thread issues the cp.async copies of its part of a tile and attaches an mbarrier arrival to them (no
+        // wait): up to nY tiles are in flight.  With ONE buffer (C >= 256) the tile is handed over in 64-channel slabs, each with its
+        // own barriers: the slabs of the next tile arrive while the last GEMM1 of this tile still reads the later ones.
         constexpr int CH = NT / 8;                       // 8-pixel chunks per channel row of a tile
         constexpr int KPP = (kLoadWarps * 32) / CH;      // channels per pass
-        const int lt = threadIdx.x - 320;
+        const int lt = threadIdx.x - kLoad0;
         const int n = lt % CH, k0 = lt / CH;
+        const bool slabs = (nY == 1);
         for (int t = 0; t < my_tiles; ++t) {
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            const uint32_t ybuf = (uint32_t)t % nY;
-            tc::mbar_wait(bar(Y_EMPTY + ybuf), (((uint32_t)t / nY) & 1u) ^ 1u);
-            if (warp == 10) stamp(3, 2 * t);
+            const uint32_t ybuf = slabs ? 0u : (uint32_t)t % nY;
+            const uint32_t yph = (slabs ? (uint32_t)t : (uint32_t)t / nY) & 1u;
             const uint32_t dst = sb + p.offY + ybuf * p.yBytes + (uint32_t)n * p.sboY;
-            const Pix px = pix_make((uint32_t)tile * NT + 8u * n, (uint32_t)HW);
-            if (VEC >= 4) {
-                const Pix px4 = pix_add(px, 4, HW);
-                const T* src0 = gy + (((long)px.b * C) * (long)HW + px.i);
-                const T* src1 = gy + (((long)px4.b * C) * (long)HW + px4.i);
-                const bool in0 = px.b < p.B && !(p.dbg & 8), in1 = px4.b < p.B && !(p.dbg & 8);
-                for (int k = k0; k < p.CP; k += KPP) {
-                    const bool kin = k < C;
-                    if (VEC == 8) cp_async16(dst + (uint32_t)k * 16u, in0 && kin ? (const void*)(src0 + (long)k * HW) : (const void*)gy, in0 && kin);
-                    else {
-                        cp_async8(dst + (uint32_t)k * 16u, in0 && kin ? (const void*)(src0 + (long)k * HW) : (const void*)gy, in0 && kin);
-                        cp_async8(dst + (uint32_t)k * 16u + 8u, in1 && kin ? (const void*)(src1 + (long)k * HW) : (const void*)gy, in1 && kin);
+            const Pix px = pix_make((uint32_t)tile * NT + 8u * n, (uint32_t)p.HWp);
+            const ChunkAddr<VEC> ca(px, (p.dbg & 8) ? 0 : p.B, C, HW);
+            const int nslab = slabs ? nK1 : 1;
+            for (int sl = 0; sl < nslab; ++sl) {
+                const uint32_t bi = slabs ? (uint32_t)sl : ybuf;
+                const int kbeg = slabs ? 64 * sl : 0, kend = slabs ? min(64 * sl + 64, p.CP) : p.CP;
+                tc::mbar_wait(bar(Y_EMPTY) + 8u * bi, yph ^ 1u);
+                if (warp == 10 && sl == 0) stamp(3, 2 * t);
+                if (VEC >= 4) {
+                    // pointer increments only: an invalid piece (pixels past the batch) reads gy[0] with size 0 = zero fill
+                    const long rowb = (long)HW * (long)sizeof(T);
+                    const char* s0 = ca.v0 ? reinterpret_cast<const char*>(gy + ca.o0) + (long)(kbeg + k0) * rowb : reinterpret_cast<const char*>(gy);
+                    const char* s1 = ca.v1 ? reinterpret_cast<const char*>(gy + ca.o1) + (long)(kbeg + k0) * rowb : reinterpret_cast<const char*>(gy);
+                    const long st0 = ca.v0 ? (long)KPP * rowb : 0, st1 = ca.v1 ? (long)KPP * rowb : 0;
+                    const uint32_t z0 = ca.v0 ? (VEC == 8 ? 16u : 8u) : 0u, z1 = ca.v1 ? 8u : 0u;
+                    uint32_t d = dst + (uint32_t)(kbeg + k0) * 16u;
+                    const int kreal = min(kend, C);
+                    int k = kbeg + k0;
+                    for (; k < kreal; k += KPP) {
+                        if (VEC == 8) cp_async16z(d, s0, z0);
+                        else { cp_async8z(d, s0, z0); cp_async8z(d + 8u, s1, z1); }
+                        s0 += st0; s1 += st1; d += (uint32_t)KPP * 16u;
                     }
-                }
-                cp_async_arrive_noinc(bar(Y_FULL + ybuf));
-            } else {
-                for (int kb = k0; kb < p.CP; kb += 4 * KPP) {
-                    uint4 v[4];
+                    for (; k < kend; k += KPP) {   // channels padded up to a multiple of 16: zeros
+                        if (VEC == 8) cp_async16z(d, gy, 0u);
+                        else { cp_async8z(d, gy, 0u); cp_async8z(d + 8u, gy, 0u); }
+                        d += (uint32_t)KPP * 16u;
+                    }
+                    cp_async_arrive_noinc(bar(Y_FULL) + 8u * bi);
+                } else {
+                    const unsigned short* row = reinterpret_cast<const unsigned short*>(gy) + ca.o0;
+                    for (int kb = kbeg + k0; kb < kend; kb += 4 * KPP) {
+                        uint4 v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = kb + u * KPP;
-                        v[u] = (k < C) ? load8<T, VEC>(gy, px, p.B, C, HW, k) : make_uint4(0u, 0u, 0u, 0u);
-                    }
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = kb + u * KPP;
+                            v[u] = (k < C) ? load8e(row + (long)k * HW, ca.nv) : make_uint4(0u, 0u, 0u, 0u);
+                        }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = kb + u * KPP;
-                        if (k < p.CP) sts128(dst + (uint32_t)k * 16u, v[u].x, v[u].y, v[u].z, v[u].w);
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = kb + u * KPP;
+                            if (k < kend) sts128(dst + (uint32_t)k * 16u, v[u].x, v[u].y, v[u].z, v[u].w);
+                        }
                     }
+                    tc::mbar_arrive(bar(Y_FULL) + 8u * bi);
                 }
-                tc::mbar_arrive(bar(Y_FULL + ybuf));
             }
             if (warp == 10) stamp(3, 2 * t + 1);
         }
         if (VEC >= 4) cp_async_wait_all();
+    } else if (warp >= 10 + kLoadWarps) {
+        // ================= output writers =================
+        // An epilogue group leaves the finished rows of a channel tile (D2 + b2, 16-bit) in its staging buffer; these warps add the
+        // residual with their lanes running ALONG the pixels (coalesced x loads and out stores) and store.  The accumulator leaves TMEM
+        // without waiting for HBM, and the epilogue warps (the scarce resource for small C) do not spend issue slots on the stores.
+        // The residual rows are fetched 8 iterations ahead, across channel-tile and tile borders of the wait for the staged rows.
+        constexpr int CH = NT / 8, RPI = 32 / CH;        // 8-pixel chunks per row; rows per warp pass
+        constexpr uint32_t SP = NT * 2 + 16;             // staging row pitch (bytes): conflict-free for both access patterns
+        constexpr int PF = 8;                            // prefetch distance (iterations); CH is a multiple of it
+        const int q = warp - (10 + kLoadWarps), no = lane % CH, rs = lane / CH;
+        const bool traffic = !(p.dbg & 4);
+        uint32_t ocnt0 = 0, ocnt1 = 0;   // staging hand-offs received from epilogue group 0 / 1
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            const uint32_t grp = (uint32_t)(t * nH + nH - 1) & 1u;   // the group that owns the tile's last hidden chunk
+            const uint32_t stage = sb + p.offH + grp * p.hBytes + (uint32_t)no * 16u;
+            const Pix pxn = pix_make((uint32_t)tile * NT + 8u * (uint32_t)no, (uint32_t)p.HWp);
+            const ChunkAddr<VEC> ca(pxn, (traffic && !(p.dbg & 16)) ? p.B : 0, C, HW);    // residual loads
+            const ChunkAddr<VEC> cs(pxn, (traffic && !(p.dbg & 32)) ? p.B : 0, C, HW);    // stores
+            const int total = nCT * CH;                  // iteration j = ct * CH + it handles row r = 32 q + it RPI + rs of channel tile ct
+            auto chan = [&](int j) { return (j / CH) * 128 + 32 * q + (j % CH) * RPI + rs; };
+            if (VEC >= 4) {
+                // Row cursors: the loop body is a shared-memory load, one or two global loads (PF iterations ahead), packed 16-bit
+                // adds, one or two stores and pointer increments.
+                const long rowb = (long)HW * (long)sizeof(T);
+                const long step_in = (long)RPI * rowb, step_ct = (long)(128 - (CH - 1) * RPI) * rowb;
+                const long first = (long)(32 * q + rs) * rowb;
+                const char* xp0 = reinterpret_cast<const char*>(gx + ca.o0) + first;   // prefetch cursors (iteration j + PF)
+                const char* xp1 = reinterpret_cast<const char*>(gx + ca.o1) + first;
+                char* wp0 = reinterpret_cast<char*>(gout + cs.o0) + first;             // store cursors (iteration j)
+                char* wp1 = reinterpret_cast<char*>(gout + cs.o1) + first;
+                uint4 xr[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const bool in = chan(u) < C;
+                    if (VEC == 8) xr[u] = ldg128p(xp0, in && ca.v0);
+                    else { const uint2 lo = ldg64p(xp0, in && ca.v0), hi = ldg64p(xp1, in && ca.v1); xr[u] = make_uint4(lo.x, lo.y, hi.x, hi.y); }
+                    const long st = ((u + 1) % CH == 0) ? step_ct : step_in;
+                    xp0 += st; xp1 += st;
+                }
+                for (int jb = 0; jb < total; jb += PF) {
+                    if (jb % CH == 0) {
+                        tc::mbar_wait(bar(OUT_FULL) + 8u * grp, (grp ? ocnt1 : ocnt0) & 1u);
+                        if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH));
+                    }
+                    const bool ct_end = (jb + PF) % CH == 0;       // the store cursor crosses a channel-tile border after this block
+                    const bool pf_end = (jb + 2 * PF) % CH == 0;   // ... the prefetch cursor does
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        const int j = jb + u, it = j % CH;
+                        uint32_t sw[4];
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)(32 * q + it * RPI + rs) * SP));
+                        const uint4 xw = xr[u];
+                        const bool in_next = (j + PF < total) && chan(j + PF) < C;
+                        if (VEC == 8) xr[u] = ldg128p(xp0, in_next && ca.v0);
+                        else { const uint2 lo = ldg64p(xp0, in_next && ca.v0), hi = ldg64p(xp1, in_next && ca.v1); xr[u] = make_uint4(lo.x, lo.y, hi.x, hi.y); }
+                        const uint4 w = make_uint4(Cvt<T>::add2(sw[0], xw.x), Cvt<T>::add2(sw[1], xw.y), Cvt<T>::add2(sw[2], xw.z), Cvt<T>::add2(sw[3], xw.w));
+                        const bool in = chan(j) < C;
+                        if (VEC == 8) stg128p(wp0, w, in && cs.v0);
+                        else { stg64p(wp0, w.x, w.y, in && cs.v0); stg64p(wp1, w.z, w.w, in && cs.v1); }
+                        const long stw = (u == PF - 1 && ct_end) ? step_ct : step_in, stx = (u == PF - 1 && pf_end) ? step_ct : step_in;
+                        xp0 += stx; xp1 += stx; wp0 += stw; wp1 += stw;
+                    }
+                    if (ct_end) {
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(bar(OUT_EMPTY) + 8u * grp);   // the staging buffer may be overwritten
+                        if (grp) ++ocnt1; else ++ocnt0;
+                        if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH) + 1);
+                    }
+                }
+            } else {
+                const unsigned short* xrow = reinterpret_cast<const unsigned short*>(gx) + ca.o0;
+                unsigned short* orow = reinterpret_cast<unsigned short*>(gout) + cs.o0;
+                uint4 xr[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) { const int c = chan(u); xr[u] = c < C ? load8e(xrow + (long)c * HW, ca.nv) : make_uint4(0u, 0u, 0u, 0u); }
+                for (int jb = 0; jb < total; jb += PF) {
+                    if (jb % CH == 0) {
+                        tc::mbar_wait(bar(OUT_FULL) + 8u * grp, (grp ? ocnt1 : ocnt0) & 1u);
+                        if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH));
+                    }
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        const int j = jb + u, it = j % CH, c = chan(j);
+                        uint32_t sw[4];
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)(32 * q + it * RPI + rs) * SP));
+                        const uint4 xw = xr[u];
+                        if (j + PF < total) { const int cn = chan(j + PF); xr[u] = cn < C ? load8e(xrow + (long)cn * HW, ca.nv) : make_uint4(0u, 0u, 0u, 0u); }
+                        const uint4 w = make_uint4(Cvt<T>::add2(sw[0], xw.x), Cvt<T>::add2(sw[1], xw.y), Cvt<T>::add2(sw[2], xw.z), Cvt<T>::add2(sw[3], xw.w));
+                        if (c < C) store8e(orow + (long)c * HW, cs.nv, w);
+                    }
+                    if ((jb + PF) % CH == 0) {
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(bar(OUT_EMPTY) + 8u * grp);   // the staging buffer may be overwritten
+                        if (grp) ++ocnt1; else ++ocnt0;
+                        if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH) + 1);
+                    }
+                }
+            }
+        }
     } else {
         // ================= epilogue warps: two groups of four, chunk g belongs to group g & 1 =================
         // A group owns D1[grp] / H[grp]: while one group runs the GELU of chunk g, the other waits for (or already works on) chunk g + 1,
@@ -383,8 +574,9 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
         const int q = warp & 3, grp = warp >> 2;
         const int row = 32 * q + lane;
         const uint32_t trow = tbase + ((uint32_t)(32 * q) << 16);
-        constexpr int NCH = NT / 8;
         const uint32_t hdst = sb + p.offH + (uint32_t)grp * p.hBytes + (uint32_t)row * 16u;
+        const uint32_t out_full = bar(OUT_FULL) + 8u * (uint32_t)grp, out_empty = bar(OUT_EMPTY) + 8u * (uint32_t)grp;
+        uint32_t out_uses = 0;       // staging hand-offs of this group so far: H[grp] doubles as its staging buffer
         int s = grp % nH, t = grp / nH;   // chunk g = grp, grp + 2, ...
         for (int g = grp; g < G; g += 2) {
             if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 0);
@@ -393,6 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
             const float bias = sb1[s * 128 + row];
             const float2 bias2v = make_float2(bias, bias);
             tc::mbar_wait(bar(H_EMPTY + grp), (use & 1u) ^ 1u);   // GEMM2 of chunk g - 2 has read this H buffer
+            tc::mbar_wait(out_empty, (out_uses & 1u) ^ 1u);        // ... and the writers have taken the last staged rows out of it
             tc::mbar_wait(bar(D1_FULL + grp), use & 1u);
             tc::fence_after_sync();
             if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 1);
@@ -417,42 +610,19 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(bar(H_FULL + grp));
             if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 2);
-            // ---- last chunk of a tile: out = D2 + b2 + x once its GEMM2 has finished (the other group works meanwhile).
-            // The accumulator rows (one channel per lane) are staged in shared memory (this group's H buffer is free by then) and
-            // leave through a second pass whose lanes run along the pixels: global loads / stores of x and out are coalesced
-            // (a row-per-lane access costs 32 L1 wavefronts per instruction and was the bottleneck of the HBM-bound stages).
+            // ---- last chunk of a tile: once its GEMM2 has finished, the accumulator rows (one channel per lane) + b2 go, as 16-bit
+            // values (the reference's conv output is a 16-bit tensor too), into the staging buffer, one channel tile at a time; the
+            // writer warps add the residual and store.  The accumulator is free again after the last tcgen05.ld: GEMM2 of the next tile
+            // does not wait for global memory.
             if (s == nH - 1) {
-                constexpr int CH = NT / 8, RPI = 32 / CH;      // 8-pixel chunks per row; rows per warp pass of the coalesced phase
-                constexpr uint32_t SP = NT * 2 + 16;           // staging row pitch (bytes): conflict-free for both access patterns
-                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-                const uint32_t db = (uint32_t)t % nD2;
-                const bool traffic = !(p.dbg & 4);
-                const int n = lane % CH, rs = lane / CH;
-                const Pix pxn = pix_make((uint32_t)tile * NT + 8u * (uint32_t)n, (uint32_t)HW);
+                constexpr uint32_t SP = NT * 2 + 16;
                 const uint32_t stage = sb + p.offH + (uint32_t)grp * p.hBytes;
-                auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
-                // the residual of the first channel tile is fetched before the wait: its latency hides under GEMM2
-                uint4 xr[NCH];
-#pragma unroll
-                for (int it = 0; it < NCH; ++it) {
-                    const int c = 32 * q + it * RPI + rs;
-                    xr[it] = (c < C && traffic) ? load8<T, VEC>(gx, pxn, p.B, C, HW, c) : make_uint4(0u, 0u, 0u, 0u);
-                }
-                tc::mbar_wait(bar(D2_FULL + db), ((uint32_t)t / nD2) & 1u);
+                const uint32_t db = nD2 == 2 ? ((uint32_t)t & 1u) : 0u, dphase = (nD2 == 2 ? ((uint32_t)t >> 1) : (uint32_t)t) & 1u;
+                tc::mbar_wait(bar(D2_FULL) + 8u * db, dphase);
                 tc::fence_after_sync();
-                group_sync();   // (the mbarrier chain already orders this group's H stores before the staging stores below; the barrier
-                                //  states it in a form compute-sanitizer's racecheck can follow)
                 if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 3);
                 for (int ct = 0; ct < nCT; ++ct) {
-                    if (ct > 0) {
-                        group_sync();   // the previous channel tile has left the staging buffer
-#pragma unroll
-                        for (int it = 0; it < NCH; ++it) {
-                            const int c = ct * 128 + 32 * q + it * RPI + rs;
-                            xr[it] = (c < C && traffic) ? load8<T, VEC>(gx, pxn, p.B, C, HW, c) : make_uint4(0u, 0u, 0u, 0u);
-                        }
-                    }
-                    // pass A: accumulator row -> + b2 -> 16-bit -> staging (the reference's conv output is a 16-bit tensor too)
+                    tc::mbar_wait(out_empty, (out_uses & 1u) ^ 1u);   // the previous channel tile has left the staging buffer
                     const float bias2 = sb2[ct * 128 + row];
 #pragma unroll
                     for (int c0 = 0; c0 < NT; c0 += 32) {
@@ -470,26 +640,13 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                             sts128(stage + (uint32_t)row * SP + (uint32_t)(c0 + 8 * ch) * 2u, w[0], w[1], w[2], w[3]);
                         }
                     }
-                    group_sync();
-                    // pass B: lanes along the pixels: out = x + staged
-#pragma unroll
-                    for (int it = 0; it < NCH; ++it) {
-                        const int r = 32 * q + it * RPI + rs, c = ct * 128 + r;
-                        uint32_t sw[4];
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)r * SP + (uint32_t)n * 16u));
-                        const uint32_t xw[4] = {xr[it].x, xr[it].y, xr[it].z, xr[it].w};
-                        uint32_t w[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 r = __fadd2_rn(Cvt<T>::unpack(sw[e]), Cvt<T>::unpack(xw[e]));
-                            w[e] = Cvt<T>::pack(r.x, r.y);
-                        }
-                        if (c < C && traffic) store8<T, VEC>(gout, pxn, p.B, C, HW, c, make_uint4(w[0], w[1], w[2], w[3]));
-                    }
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(out_full);
+                    ++out_uses;
                 }
                 tc::fence_before_sync();
-                group_sync();   // staging reads are done before this group's next GELU overwrites the buffer
-                if (lane == 0) tc::mbar_arrive(bar(D2_EMPTY + db));
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(bar(D2_EMPTY) + 8u * db);
                 if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 4);
             }
             s += 2;
@@ -541,8 +698,6 @@ int ffn_tc_make_plan(FfnTcPlan& p, int B, int C, int HID, int HW, int dtype, int
     if (!(dtype == 1 || dtype == 2) || B < 1 || C < 8 || HID < 1 || HW < 1 || (C % 8) != 0) return 1;
     p = FfnTcPlan{};
     p.B = B; p.C = C; p.HID = HID; p.HW = HW; p.dtype = dtype;
-    p.P = (long)B * HW;
-    if (p.P + 65536 >= (1l << 31)) return 1;   // pixel indices are 32-bit
     p.CP = (C + 15) / 16 * 16;
     p.HIDP = (HID + 127) / 128 * 128;
     p.nH = p.HIDP / 128;
@@ -553,6 +708,9 @@ int ffn_tc_make_plan(FfnTcPlan& p, int B, int C, int HID, int HW, int dtype, int
     if (2 * p.NT + p.nCT * p.NT > 512) return 1;          // TMEM columns: D1 x 2 + D2 x nCT
     p.nD2 = (2 * p.NT + 2 * p.nCT * p.NT <= 512) ? 2 : 1;  // a second output accumulator when TMEM has room (C <= 128)
     p.vec = (HW % 8 == 0) ? 8 : ((HW % 4 == 0) ? 4 : 1);
+    p.HWp = p.vec == 1 ? (HW + 7) / 8 * 8 : HW;
+    p.P = (long)B * p.HWp;
+    if (p.P + 65536 >= (1l << 31)) return 1;   // pixel indices are 32-bit
     p.sboY = (uint32_t)p.CP * 16u + 16u;
     p.yBytes = ((uint32_t)(p.NT / 8) * p.sboY + 127u) / 128u * 128u;
     p.hBytes = (uint32_t)(p.NT / 8) * kSboH;

@@ -8,7 +8,8 @@ namespace recnext {
 
 struct FfnTcPlan {
     int B, C, CP, HID, HIDP, HW, dtype;
-    long P;                 // pixels of the whole batch
+    int HWp;                // pixel columns one image takes in tile space: HW, or HW rounded up to 8 when vec = 1 (no 8-pixel chunk straddles two images)
+    long P;                 // pixel columns of the whole batch (B x HWp)
     int NT;                 // pixels per tile (128, or 64 for C > 256: TMEM holds D1 x 2 + D2 x ceil(C / 128) accumulators of NT columns)
     int nH, nK1, kwLast, nCT;  // hidden chunks of 128 rows; K tiles (64 wide, the last kwLast wide) of W1; 128-row tiles of W2
     int vec;                // pixels per global access: 8 (HW % 8 == 0), 4 (HW % 4 == 0) or 1

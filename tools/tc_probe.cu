@@ -204,6 +204,47 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int N, int nrep, int mode,
             t1 = clock64();
             if (lane == 0) { res[0] = t1 - t0; res[1] = t1 - t0; res[2] = 1; }
         }
+    } else if (mode == 11) {
+        // the channel mixer's GEMM1 operand walk: A = four 16 KB K-major weight tiles (ring slots), B = MN-major activation tile with
+        // chunk pitch `a_sbo` bytes (C * 16 + 16 in ffn_tc.cu), 4 K steps per slot
+        if (uwarp == 0) {
+            uint32_t elected = 0;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+            const uint32_t idesc_mn = tc::make_idesc(128, N, 1, 0, 1);
+            t0 = clock64();
+            for (int i = 0; i < nrep; ++i) {
+                const int kc = i & 3;
+                const uint64_t a0 = tc::make_sdesc(tc::smem_u32(smem) + kc * 16384, 2048, 128);
+                const uint64_t b0 = tc::make_sdesc(tc::smem_u32(smem) + 65536 + (uint32_t)(kc * 64) * 16u, 128, a_sbo);
+                for (int j = 0; j < 4; ++j)
+                    if (elected) tc::mma_ss(tbase + (i & 1) * N, tc::sdesc_advance(a0, (uint32_t)j * 4096u), tc::sdesc_advance(b0, (uint32_t)j * 256u), idesc_mn, 1);
+                if (elected) tc::mma_commit(bar1);
+            }
+            if (elected) tc::mma_commit(bar0);
+            t1 = clock64();
+            bool ok = false;
+            for (int it = 0; it < (1 << 24); ++it) if (tc::mbar_try_wait(bar0, 0)) { ok = true; break; }
+            t2 = clock64();
+            if (lane == 0) { res[0] = t1 - t0; res[1] = t2 - t0; res[2] = ok ? 1 : 0; }
+        }
+    } else if (mode == 12 || mode == 13) {
+        // wake-up latency of an mbarrier wait: warp 1 arrives after `nrep` clocks; warp 0 waits (mode 12: try_wait with the suspend-time
+        // hint of tc05.cuh; mode 13: try_wait without a hint in a spin loop) and stamps the clock when it gets through
+        __shared__ long long t_arrive;
+        if (uwarp == 1) {
+            const long long s0 = clock64();
+            while (clock64() - s0 < nrep) { }
+            if (lane == 0) { t_arrive = clock64(); tc::mbar_arrive(bar0); }
+        } else if (uwarp == 0) {
+            if (mode == 12) tc::mbar_wait(bar0, 0);
+            else {
+                uint32_t ok = 0;
+                while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar0), "r"(0) : "memory");
+            }
+            t1 = clock64();
+            __syncwarp();
+            if (lane == 0) { res[0] = t1 - t_arrive; res[2] = 1; }
+        }
     } else if (mode == 3) {
         if (tid == 0) {
             t0 = clock64();
@@ -344,7 +385,9 @@ int main() {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("[%s] KERNEL ERROR %s\n", name, cudaGetErrorString(e)); exit(4); }
         long long r[16]; CK(cudaMemcpy(r, dres, sizeof r, cudaMemcpyDeviceToHost));
-        if (mode >= 8) printf("[time %s] N=%d groups=%d issue time %lld cyc (%.1f per group of 4 MMAs; math floor %.0f)\n", name, N, nrep, r[0], (double)r[0] / nrep, 4.0 * (N >= 128 ? N / 2.0 : (N == 64 ? 48.0 : 39.0)));
+        if (mode == 12 || mode == 13) printf("[time %s] waited %d clocks, woke %lld clocks after the arrive\n", name, nrep, r[0]);
+        else if (mode == 11) printf("[time %s] N=%d groups=%d B chunk pitch %u: total %lld cyc (%.1f per MMA) ok=%lld\n", name, N, nrep, sbo, r[1], (double)r[1] / (4.0 * nrep), r[2]);
+        else if (mode >= 8) printf("[time %s] N=%d groups=%d issue time %lld cyc (%.1f per group of 4 MMAs; math floor %.0f)\n", name, N, nrep, r[0], (double)r[0] / nrep, 4.0 * (N >= 128 ? N / 2.0 : (N == 64 ? 48.0 : 39.0)));
         else if (mode >= 5) printf("[time %s] N=%d nrep=%d total=%lld cyc (%.1f / MMA) ok=%lld  neighbour 16-byte accesses per warp: %lld %lld %lld (%.1f B/cyc)\n", name, N, nrep, r[1], (double)r[1] / nrep, r[2], r[7], r[11], r[15], 16.0 * 32 * (r[7] + r[11] + r[15]) / (double)r[1]);
         else if (mode == 0 || mode == 3) printf("[time %s] N=%d nrep=%d issue=%lld cyc total=%lld cyc (%.1f / MMA) ok=%lld\n", name, N, nrep, r[0], r[1] ? r[1] : r[0], (double)(r[1] ? r[1] : r[0]) / nrep, r[2]);
         else if (mode == 1) printf("[time %s] N=%d nrep=%d x2 issuers: w0 total=%lld w1 total=%lld (%.1f cyc / MMA overall) ok=%lld,%lld\n", name, N, nrep, r[1], r[5], (double)(r[1] > r[5] ? r[1] : r[5]) / (2.0 * nrep), r[2], r[6]);
@@ -368,6 +411,13 @@ int main() {
         timeit("4mma_n128_commit", 128, 256, 8, 128, 2048);
         timeit("4mma_n128_wait_fence_commit", 128, 256, 9, 128, 2048);
         timeit("4mma_n64_commit", 64, 256, 8, 128, 2048);
+        timeit("gemm1_walk_pitch1040", 128, 256, 11, 1040, 0);
+        timeit("gemm1_walk_pitch4112", 128, 256, 11, 4112, 0);
+        timeit("gemm1_walk_pitch4096", 128, 256, 11, 4096, 0);
+        timeit("gemm1_walk_pitch4224", 128, 256, 11, 4224, 0);
+        timeit("gemm1_walk_pitch2064", 128, 256, 11, 2064, 0);
+        timeit("gemm1_walk_n64_pitch8208", 64, 256, 11, 8208, 0);
+        for (int d : {300, 3000, 30000, 300000}) { timeit("wake_hint", 16, d, 12, 0, 0); timeit("wake_spin", 16, d, 13, 0, 0); }
         timeit("tmem_ld", 512, 64, 2, 128, 2048);
         timeit("tmem_ld_pipelined4", 512, 64, 4, 128, 2048);
         timeit("roundtrip_n16", 16, 256, 3, 128, 2048);
