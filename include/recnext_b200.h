@@ -149,6 +149,20 @@ RECNEXT_API int recnext_ffn_forward_packed(int32_t B, int32_t C, int32_t hidden,
                                            const void* packed, const float* b1, const float* b2, void* out, void* stream);
 
 /*
+ * The stem (SURVEY.md §8 f: the caller in front of the first RecConv stage): ConvNorm(3 -> C1, 3x3, stride 2, pad 1) -> GELU ->
+ * ConvNorm(C1 -> C2, 3x3, stride 2, pad 1) with both BatchNorms folded by the caller — replaces
+ *     self.stem(x)                         model/recnext.py:139-146
+ * as one kernel: the intermediate map stays in shared memory.  x: [B, 3, H, W], out: [B, C2, H2, W2] with H1 = (H-1)/2+1,
+ * H2 = (H1-1)/2+1, 16-bit dtype (RECNEXT_BF16 | RECNEXT_F16), fp32 accumulation, intermediates rounded where the reference's
+ * autocast graph rounds them.  Weights in the kernel's operand order (what recnext_b200.model.stem_pack writes), 16-byte aligned:
+ *   w1p [C1P][32]      k = ci * 9 + ky * 3 + kx, zero padded; C1P = 32 (C1 <= 32) or 48        b1p [C1P] fp32
+ *   w2p [C2P][9 C1P]   k = (ky * 3 + kx) * C1P + ci, zero padded; C2P = C2 rounded up to 16     b2p [C2P] fp32
+ * Inference entry point.  RECNEXT_EUNSUPPORTED for fp32 activations, C1 > 48 or C2 > 80 (the caller keeps its conv path).
+ */
+RECNEXT_API int recnext_stem_forward(int32_t B, int32_t H, int32_t W, int32_t C1, int32_t C2, int32_t dtype, const void* x, const void* w1p,
+                                     const float* b1p, const void* w2p, const float* b2p, void* out, void* stream);
+
+/*
  * Token mixer of a `Downsample` block: depthwise 7x7 stride-2 conv with channel multiplier 2 and the
  * eval-mode BatchNorm that follows it folded into (w, b) by the caller — replaces
  *     self.norm(self.token_mixer(x))      model/recnext.py:137-138,145

@@ -13,6 +13,7 @@
 #include "mbplan.h"
 #include "gstream.h"
 #include "ffn_tc.h"
+#include "stem.h"
 #include "devcfg.h"
 #include <stdlib.h>
 
@@ -408,6 +409,21 @@ RECNEXT_API int recnext_ffn_forward(int32_t B, int32_t C, int32_t hidden, int32_
                     "(2C + hidden) pixel-tile rows in 227 KB of shared memory (got C=%d hidden=%d HW=%d dtype=%d)", C, hidden, HW, dtype);
     const cudaError_t e = ffn_launch(pl, y, x, w1, b1, w2, b2, out, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recnext_ffn_forward: %s", cudaGetErrorString(e));
+    return RECNEXT_OK;
+}
+
+// ---- fused stem (stem.cu)
+RECNEXT_API int recnext_stem_forward(int32_t B, int32_t H, int32_t W, int32_t C1, int32_t C2, int32_t dtype, const void* x, const void* w1p,
+                                     const float* b1p, const void* w2p, const float* b2p, void* out, void* stream) {
+    if (B < 0 || H < 1 || W < 1 || C1 < 1 || C2 < 1) return fail(RECNEXT_EINVAL, "recnext_stem_forward: bad shape [%d,3,%d,%d] -> %d -> %d channels", B, H, W, C1, C2);
+    if (B == 0) return RECNEXT_OK;
+    if (!x || !w1p || !b1p || !w2p || !b2p || !out) return fail(RECNEXT_EINVAL, "recnext_stem_forward: null tensor");
+    if ((((uintptr_t)w1p | (uintptr_t)w2p) & 15) != 0) return fail(RECNEXT_EINVAL, "recnext_stem_forward: packed weights must be 16-byte aligned");
+    StemPlan pl;
+    if (stem_make_plan(pl, B, H, W, C1, C2, dtype, device_sms()))
+        return fail(RECNEXT_EUNSUPPORTED, "recnext_stem_forward: needs 16-bit activations, C1 <= 48 and C2 <= 80 (got C1=%d C2=%d dtype=%d)", C1, C2, dtype);
+    const cudaError_t e = stem_launch(pl, x, w1p, b1p, w2p, b2p, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "recnext_stem_forward: %s", cudaGetErrorString(e));
     return RECNEXT_OK;
 }
 

@@ -198,12 +198,78 @@ def mlp(cin: int, hidden: int, act_layer=nn.GELU) -> nn.Sequential:
     return nn.Sequential(ConvNorm(cin, hidden, 1), act_layer(), ConvNorm(hidden, cin, 1))
 
 
+FUSED_STEM = os.environ.get("RECNEXT_STEM", "1") != "0"
+
+
+def stem_pack(conv1: nn.Conv2d, conv2: nn.Conv2d, dtype):
+    """Weights of the fused stem kernel from the two (BatchNorm-folded) 3x3 stride-2 convs:
+    w1p [C1P, 32] with k = ci * 9 + ky * 3 + kx, w2p [C2P, 9 * C1P] with k = (ky * 3 + kx) * C1P + ci, zero padded; fp32 biases."""
+    with torch.no_grad():
+        C1, C2 = conv1.out_channels, conv2.out_channels
+        C1P, C2P = (32 if C1 <= 32 else 48), (C2 + 15) // 16 * 16
+        dev = conv1.weight.device
+        w1p = torch.zeros(C1P, 32, device=dev, dtype=torch.float32)
+        w1p[:C1, :27] = conv1.weight.float().reshape(C1, 27)
+        w2p = torch.zeros(C2P, 9, C1P, device=dev, dtype=torch.float32)
+        w2p[:C2, :, :C1] = conv2.weight.float().permute(0, 2, 3, 1).reshape(C2, 9, C1)
+        b1p = torch.zeros(C1P, device=dev, dtype=torch.float32)
+        b1p[:C1] = conv1.bias.float()
+        b2p = torch.zeros(C2P, device=dev, dtype=torch.float32)
+        b2p[:C2] = conv2.bias.float()
+        return w1p.to(dtype).contiguous(), b1p, w2p.reshape(C2P, 9 * C1P).to(dtype).contiguous(), b2p, C1, C2
+
+
+def stem_forward(x: torch.Tensor, w1p, b1p, w2p, b2p, C1: int, C2: int) -> torch.Tensor:
+    """conv 3x3 s2 -> GELU -> conv 3x3 s2 of the stem (reference model/recnext.py:139-146, ConvNorms folded) as ONE sm_100a kernel
+    (``recnext_stem_forward``): the 112 x 112 intermediate never leaves shared memory.  x: [B, 3, H, W] 16-bit CUDA tensor."""
+    if not x.is_cuda:
+        raise RuntimeError("recnext_b200.stem_forward runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if x.dtype not in (torch.bfloat16, torch.float16) or x.dim() != 4 or x.shape[1] != 3:
+        raise TypeError("stem_forward: x must be a 16-bit [B, 3, H, W] tensor")
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    H2, W2 = ((H - 1) // 2) // 2 + 1, ((W - 1) // 2) // 2 + 1
+    out = torch.empty(B, C2, H2, W2, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        ev = _timing_start()
+        N.check(N.lib().recnext_stem_forward(B, H, W, C1, C2, _DTYPES[x.dtype], x.data_ptr(), w1p.data_ptr(), b1p.data_ptr(), w2p.data_ptr(),
+                                             b2p.data_ptr(), out.data_ptr(), _stream(x)), "recnext_stem_forward")
+        _timing_stop(ev, (x.numel() + out.numel()) * x.element_size(), ("stem",) + tuple(x.shape))
+    return out
+
+
 class RecNextStem(nn.Module):
     def __init__(self, cin, cout, act_layer=nn.GELU):
         super().__init__()
         self.stem = nn.Sequential(ConvNorm(cin, cout // 2, 3, 2, 1), act_layer(), ConvNorm(cout // 2, cout, 3, 2, 1))
 
+    def train(self, mode: bool = True):
+        self._stem_cache = None
+        return super().train(mode)
+
+    def _fused_ok(self, x) -> bool:
+        """Eval mode, ConvNorms folded (fuse()), 16-bit compute, no gradient wanted: the fused kernel takes the stem."""
+        if self.training or not x.is_cuda or not FUSED_STEM or torch.jit.is_tracing() or x.dim() != 4 or x.shape[1] != 3:
+            return False
+        c1, act, c2 = self.stem[0], self.stem[1], self.stem[2]
+        if not (type(c1) is nn.Conv2d and type(c2) is nn.Conv2d and c1.bias is not None and c2.bias is not None):
+            return False
+        if not isinstance(act, nn.GELU) or getattr(act, "approximate", "none") != "none":
+            return False
+        if c1.out_channels > 48 or c2.out_channels > 80 or c1.in_channels != 3:
+            return False
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        return dt in (torch.bfloat16, torch.float16) and not _needs_autograd(x, self)
+
     def forward(self, x):
+        if self._fused_ok(x):
+            dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+            key = (dt, x.device, _param_key(self.stem[0], self.stem[2]))
+            c = getattr(self, "_stem_cache", None)
+            if c is None or c[0] != key:
+                c = (key, stem_pack(self.stem[0], self.stem[2], dt))
+                self._stem_cache = c
+            return stem_forward(x.to(dt), *c[1])
         return self.stem(x)
 
 
