@@ -121,18 +121,7 @@ static long long* prof_buffer() {
     return g_prof;
 }
 
-// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
-static int device_sms() {
-    static int sms[kMaxDevices] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;  // planning without a visible device (plan_describe on a CPU box)
-    if (sms[dev] == 0) {
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms[dev] = v;
-        else return 148;
-    }
-    return sms[dev];
-}
+static int device_sms() { return rc_device_sms(); }   // (planning without a visible device, e.g. plan_describe on a CPU box: 148)
 
 static int check_desc(const recconv_desc* d) {
     if (!d) return fail(RECNEXT_EINVAL, "recconv: null descriptor");

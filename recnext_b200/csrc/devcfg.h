@@ -25,4 +25,17 @@ inline cudaError_t rc_once_per_device(DeviceOnce& flags, F f) {
     return e;
 }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs); 148 when no device is visible
+inline int rc_device_sms() {
+    static int sms[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms[dev] = v;
+        else return 148;
+    }
+    return sms[dev];
+}
+
 }  // namespace recnext

@@ -444,7 +444,7 @@ class Downsample(nn.Module):
     def forward(self, x):
         dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         if (not self.training and x.is_cuda and FUSED_FFN and dt in (torch.bfloat16, torch.float16) and not torch.jit.is_tracing()
-                and not _needs_autograd(x, self) and (x.shape[2] + 8) * (x.shape[3] + 9) * 4 + 448 <= 227 * 1024):
+                and not _needs_autograd(x, self) and (x.shape[2] + 8) * ((x.shape[3] + 7) // 8 + 10) * 32 + 448 <= 227 * 1024):
             x = dwdown_forward(x.to(dt), *self._dw_params(x.device))   # norm(token_mixer(x)): one kernel, BatchNorm folded
         else:
             x = self.norm(self.token_mixer(x))

@@ -118,7 +118,8 @@ def test_block_with_fused_ffn_matches_library_path(monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(4, 64, 56, 56), (3, 128, 28, 28), (3, 256, 14, 14), (2, 40, 56, 56), (2, 6, 9, 13), (1, 3, 25, 42), (2, 4, 7, 7)],
+@pytest.mark.parametrize("shape", [(4, 64, 56, 56), (3, 128, 28, 28), (3, 256, 14, 14), (2, 40, 56, 56), (2, 6, 9, 13), (1, 3, 25, 42), (2, 4, 7, 7), (1, 8, 112, 112), (2, 16, 30, 20),
+                                   (40, 7, 14, 14), (1, 2, 1, 1), (1, 5, 2, 3)],
                          ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
 def test_dwdown_kernel_vs_torch(shape, dtype):
