@@ -315,12 +315,17 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
         // four (or `steps`) K steps of one ring slot: D (+)= A[slot] . B
         long long acc_wait = 0, acc_issue = 0, acc_slots = 0;
         const bool profiling = prof != nullptr && blockIdx.x == 0;
+        // The barrier of the NEXT slot is probed (non-blocking) before this slot's MMAs are issued: the probe's ~100-clock latency
+        // passes while the tensor pipe takes the MMAs, instead of in front of the next slot.
+        bool have = false;                          // W_FULL of the current slot has already been observed
         auto slot_mmas = [&](uint32_t d, uint64_t bd, bool fresh, int steps) {
             long long c0 = 0, c1 = 0;
             if (profiling) c0 = clock64();
-            tc::mbar_wait(wfull0 + 8u * wslot, wphase);
+            if (!have) tc::mbar_wait(wfull0 + 8u * wslot, wphase);
             tc::fence_after_sync();
             if (profiling) c1 = clock64();
+            const uint32_t nslot = wslot + 1 == (uint32_t)RS ? 0u : wslot + 1, nphase = wslot + 1 == (uint32_t)RS ? wphase ^ 1u : wphase;
+            const bool next_ready = tc::mbar_test_wait(wfull0 + 8u * nslot, nphase);
             const uint64_t ad = a_ring + (uint64_t)(wslot * (kTileBytes / 16));
             if (steps == 4) {
                 if (leader) {
@@ -338,7 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                 else mma_commit_mcast(wempty0 + 8u * wslot, cmask);
             }
             if (profiling) { const long long c2 = clock64(); acc_wait += c1 - c0; acc_issue += c2 - c1; ++acc_slots; }
-            if (++wslot == (uint32_t)RS) { wslot = 0; wphase ^= 1u; }
+            have = next_ready;
+            wslot = nslot; wphase = nphase;
         };
         int s = 0;                                  // chunk g = (tile of this CTA, hidden chunk s)
         uint32_t ybuf = 0, yphase = 0;              // activation buffer of chunk g's tile
@@ -486,14 +492,19 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
             const Pix pxn = pix_make((uint32_t)tile * NT + 8u * (uint32_t)no, (uint32_t)p.HWp);
             const ChunkAddr<VEC> ca(pxn, (traffic && !(p.dbg & 16)) ? p.B : 0, C, HW);    // residual loads
             const ChunkAddr<VEC> cs(pxn, (traffic && !(p.dbg & 32)) ? p.B : 0, C, HW);    // stores
-            const int total = nCT * CH;                  // iteration j = ct * CH + it handles row r = 32 q + it RPI + rs of channel tile ct
-            auto chan = [&](int j) { return (j / CH) * 128 + 32 * q + (j % CH) * RPI + rs; };
+            // Pass j = ct * CH + it: the four warps take the rows [4 RPI it, 4 RPI (it + 1)) of channel tile ct, RPI rows each, so narrow
+            // tensors (C = 64: half a channel tile) keep every warp busy; the last channel tile stops after its last valid row
+            // (rounded up to the prefetch block).
+            const int last_rows = C - (nCT - 1) * 128;
+            const int total = (nCT - 1) * CH + min(CH, ((last_rows + 4 * RPI - 1) / (4 * RPI) + PF - 1) / PF * PF);
+            auto rowof = [&](int j) { return (j % CH) * (4 * RPI) + q * RPI + rs; };
+            auto chan = [&](int j) { return (j / CH) * 128 + rowof(j); };
             if (VEC >= 4) {
                 // Row cursors: the loop body is a shared-memory load, one or two global loads (PF iterations ahead), packed 16-bit
                 // adds, one or two stores and pointer increments.
                 const long rowb = (long)HW * (long)sizeof(T);
-                const long step_in = (long)RPI * rowb, step_ct = (long)(128 - (CH - 1) * RPI) * rowb;
-                const long first = (long)(32 * q + rs) * rowb;
+                const long step = (long)(4 * RPI) * rowb;             // (a channel-tile border is just the next pass: passes tile the rows)
+                const long first = (long)(q * RPI + rs) * rowb;
                 const char* xp0 = reinterpret_cast<const char*>(gx + ca.o0) + first;   // prefetch cursors (iteration j + PF)
                 const char* xp1 = reinterpret_cast<const char*>(gx + ca.o1) + first;
                 char* wp0 = reinterpret_cast<char*>(gout + cs.o0) + first;             // store cursors (iteration j)
@@ -504,21 +515,19 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                     const bool in = chan(u) < C;
                     if (VEC == 8) xr[u] = ldg128p(xp0, in && ca.v0);
                     else { const uint2 lo = ldg64p(xp0, in && ca.v0), hi = ldg64p(xp1, in && ca.v1); xr[u] = make_uint4(lo.x, lo.y, hi.x, hi.y); }
-                    const long st = ((u + 1) % CH == 0) ? step_ct : step_in;
-                    xp0 += st; xp1 += st;
+                    xp0 += step; xp1 += step;
                 }
                 for (int jb = 0; jb < total; jb += PF) {
                     if (jb % CH == 0) {
                         tc::mbar_wait(bar(OUT_FULL) + 8u * grp, (grp ? ocnt1 : ocnt0) & 1u);
                         if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH));
                     }
-                    const bool ct_end = (jb + PF) % CH == 0;       // the store cursor crosses a channel-tile border after this block
-                    const bool pf_end = (jb + 2 * PF) % CH == 0;   // ... the prefetch cursor does
+                    const bool ct_end = (jb + PF) % CH == 0 || jb + PF == total;   // this channel tile's staged rows are done after this block
 #pragma unroll
                     for (int u = 0; u < PF; ++u) {
                         const int j = jb + u, it = j % CH;
                         uint32_t sw[4];
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)(32 * q + it * RPI + rs) * SP));
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)rowof(j) * SP));
                         const uint4 xw = xr[u];
                         const bool in_next = (j + PF < total) && chan(j + PF) < C;
                         if (VEC == 8) xr[u] = ldg128p(xp0, in_next && ca.v0);
@@ -527,8 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                         const bool in = chan(j) < C;
                         if (VEC == 8) stg128p(wp0, w, in && cs.v0);
                         else { stg64p(wp0, w.x, w.y, in && cs.v0); stg64p(wp1, w.z, w.w, in && cs.v1); }
-                        const long stw = (u == PF - 1 && ct_end) ? step_ct : step_in, stx = (u == PF - 1 && pf_end) ? step_ct : step_in;
-                        xp0 += stx; xp1 += stx; wp0 += stw; wp1 += stw;
+                        xp0 += step; xp1 += step; wp0 += step; wp1 += step;
                     }
                     if (ct_end) {
                         __syncwarp();
@@ -552,13 +560,13 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                     for (int u = 0; u < PF; ++u) {
                         const int j = jb + u, it = j % CH, c = chan(j);
                         uint32_t sw[4];
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)(32 * q + it * RPI + rs) * SP));
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)rowof(j) * SP));
                         const uint4 xw = xr[u];
                         if (j + PF < total) { const int cn = chan(j + PF); xr[u] = cn < C ? load8e(xrow + (long)cn * HW, ca.nv) : make_uint4(0u, 0u, 0u, 0u); }
                         const uint4 w = make_uint4(Cvt<T>::add2(sw[0], xw.x), Cvt<T>::add2(sw[1], xw.y), Cvt<T>::add2(sw[2], xw.z), Cvt<T>::add2(sw[3], xw.w));
                         if (c < C) store8e(orow + (long)c * HW, cs.nv, w);
                     }
-                    if ((jb + PF) % CH == 0) {
+                    if ((jb + PF) % CH == 0 || jb + PF == total) {
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(bar(OUT_EMPTY) + 8u * grp);   // the staging buffer may be overwritten
                         if (grp) ++ocnt1; else ++ocnt0;

@@ -107,6 +107,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (mbarrier.test_wait): has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // A wait that outlives 2^22 probes (each probe sleeps up to the hint) can only be a protocol bug: trap (the launch fails with a
 // CUDA error) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
