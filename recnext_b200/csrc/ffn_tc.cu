@@ -82,6 +82,12 @@ __device__ __forceinline__ bool elect_one() {
     return e != 0;
 }
 
+// Named barriers that restate, in a form compute-sanitizer's racecheck can follow, orderings the mbarrier chains already guarantee
+// (staging-buffer hand-offs between an epilogue group and the writer warps).  They never block: every arrival has happened by the
+// time the matching mbarrier wait has returned.
+__device__ __forceinline__ void nb_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -520,6 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                 for (int jb = 0; jb < total; jb += PF) {
                     if (jb % CH == 0) {
                         tc::mbar_wait(bar(OUT_FULL) + 8u * grp, (grp ? ocnt1 : ocnt0) & 1u);
+                        nb_sync(3u + grp, 256u);
                         if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH));
                     }
                     const bool ct_end = (jb + PF) % CH == 0 || jb + PF == total;   // this channel tile's staged rows are done after this block
@@ -540,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                     }
                     if (ct_end) {
                         __syncwarp();
+                        nb_arrive(5u + grp, 256u);
                         if (lane == 0) tc::mbar_arrive(bar(OUT_EMPTY) + 8u * grp);   // the staging buffer may be overwritten
                         if (grp) ++ocnt1; else ++ocnt0;
                         if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH) + 1);
@@ -554,6 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                 for (int jb = 0; jb < total; jb += PF) {
                     if (jb % CH == 0) {
                         tc::mbar_wait(bar(OUT_FULL) + 8u * grp, (grp ? ocnt1 : ocnt0) & 1u);
+                        nb_sync(3u + grp, 256u);
                         if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH));
                     }
 #pragma unroll
@@ -568,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                     }
                     if ((jb + PF) % CH == 0 || jb + PF == total) {
                         __syncwarp();
+                        nb_arrive(5u + grp, 256u);
                         if (lane == 0) tc::mbar_arrive(bar(OUT_EMPTY) + 8u * grp);   // the staging buffer may be overwritten
                         if (grp) ++ocnt1; else ++ocnt0;
                         if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH) + 1);
@@ -585,6 +595,11 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
         const uint32_t hdst = sb + p.offH + (uint32_t)grp * p.hBytes + (uint32_t)row * 16u;
         const uint32_t out_full = bar(OUT_FULL) + 8u * (uint32_t)grp, out_empty = bar(OUT_EMPTY) + 8u * (uint32_t)grp;
         uint32_t out_uses = 0;       // staging hand-offs of this group so far: H[grp] doubles as its staging buffer
+        uint32_t out_synced = 0;     // ... of which the writers' release has been consumed on the named barrier (racecheck's view)
+        auto wait_drained = [&]() {  // the writers have taken the last staged rows out of H[grp]
+            tc::mbar_wait(out_empty, (out_uses & 1u) ^ 1u);
+            while (out_synced < out_uses) { nb_sync(5u + (uint32_t)grp, 256u); ++out_synced; }
+        };
         int s = grp % nH, t = grp / nH;   // chunk g = grp, grp + 2, ...
         for (int g = grp; g < G; g += 2) {
             if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 0);
@@ -593,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
             const float bias = sb1[s * 128 + row];
             const float2 bias2v = make_float2(bias, bias);
             tc::mbar_wait(bar(H_EMPTY + grp), (use & 1u) ^ 1u);   // GEMM2 of chunk g - 2 has read this H buffer
-            tc::mbar_wait(out_empty, (out_uses & 1u) ^ 1u);        // ... and the writers have taken the last staged rows out of it
+            wait_drained();                                       // ... and the writers have taken the last staged rows out of it
             tc::mbar_wait(bar(D1_FULL + grp), use & 1u);
             tc::fence_after_sync();
             if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 1);
@@ -628,9 +643,11 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                 const uint32_t db = nD2 == 2 ? ((uint32_t)t & 1u) : 0u, dphase = (nD2 == 2 ? ((uint32_t)t >> 1) : (uint32_t)t) & 1u;
                 tc::mbar_wait(bar(D2_FULL) + 8u * db, dphase);
                 tc::fence_after_sync();
+                nb_sync(1u + (uint32_t)grp, 128u);   // (this group's H stores of the last chunk precede the staging stores below: the mbarrier chain
+                                                     //  H_FULL -> GEMM2 -> D2_FULL orders them; stated for racecheck)
                 if (q == 0) stamp(1 + grp, 6 * (g >> 1) + 3);
                 for (int ct = 0; ct < nCT; ++ct) {
-                    tc::mbar_wait(out_empty, (out_uses & 1u) ^ 1u);   // the previous channel tile has left the staging buffer
+                    wait_drained();                                  // the previous channel tile has left the staging buffer
                     const float bias2 = sb2[ct * 128 + row];
 #pragma unroll
                     for (int c0 = 0; c0 < NT; c0 += 32) {
@@ -649,6 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                         }
                     }
                     __syncwarp();
+                    nb_arrive(3u + (uint32_t)grp, 256u);
                     if (lane == 0) tc::mbar_arrive(out_full);
                     ++out_uses;
                 }

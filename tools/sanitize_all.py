@@ -2,7 +2,7 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import recnext_b200 as R
-from recnext_b200.model import dwdown_forward, ffn_forward
+from recnext_b200.model import dwdown_forward, ffn_forward, RecNextStem, replace_batchnorm, stem_forward, stem_pack
 from recnext_b200.recattn import linattn_forward
 torch.manual_seed(0)
 dev = "cuda"
@@ -27,7 +27,11 @@ for (B, C, H) in [(2, 64, 28), (2, 128, 14), (2, 256, 14), (1, 320, 14), (1, 48,
     yy = torch.randn(B, C, H, H, device=dev).bfloat16(); xx = torch.randn_like(yy)
     o = ffn_forward(yy, xx, torch.randn(hid, C, device=dev).bfloat16() * 0.1, torch.randn(hid, device=dev), torch.randn(C, hid, device=dev).bfloat16() * 0.1, torch.randn(C, device=dev))
     print("ffn", (B, C, H), float(o.float().abs().mean()))
-for (B, C, H, W) in [(2, 8, 56, 56), (3, 16, 14, 14), (1, 4, 9, 13)]:
+for (B, C, H, W) in [(2, 64, 64, 64), (1, 80, 33, 47), (2, 40, 8, 8)]:
+    st = replace_batchnorm(RecNextStem(3, C).eval().to(dev))
+    o = stem_forward(torch.randn(B, 3, H, W, device=dev).bfloat16(), *stem_pack(st.stem[0], st.stem[2], torch.bfloat16))
+    print("stem", (B, C, H, W), float(o.float().abs().mean()))
+for (B, C, H, W) in [(2, 8, 56, 56), (3, 16, 14, 14), (1, 4, 9, 13), (40, 3, 28, 28), (2, 4, 30, 20)]:
     for dt in (torch.float32, torch.bfloat16):
         o = dwdown_forward(torch.randn(B, C, H, W, device=dev).to(dt), torch.randn(2 * C, 1, 7, 7, device=dev) / 7, torch.randn(2 * C, device=dev))
     print("dwdown", (B, C, H, W), float(o.float().abs().mean()))
