@@ -515,7 +515,7 @@ def main():
     per_shape, dom = [], {"bytes": 0, "ms": 0.0, "n": 0}
     for shape, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
         if isinstance(shape[0], str):   # RecAttn2d pieces: ("down" | "up", B, C, H, W)
-            kern = {"ffn": "recnext_ffn_tc_kernel", "dwdown": "recnext_dwdown_kernel"}.get(shape[0], "recconv_mfwd_kernel/" + shape[0])
+            kern = {"ffn": "recnext_ffn_tc_kernel", "dwdown": "recnext_dwdown16_kernel", "stem": "recnext_stem_kernel"}.get(shape[0], "recconv_mfwd_kernel/" + shape[0])
         else:
             level = {56: 4, 28: 3, 14: 2, 7: 1}.get(shape[2], 0) if RES == 224 else None
             desc = RC.plan_describe(shape, 5, level, "bilinear", torch.bfloat16, False, False) if level is not None else ""
@@ -569,8 +569,9 @@ def main():
                         "achieved": round(tf, 1), "peak": tpeak, "unit": "TFLOP/s", "frac": round(tf / tpeak, 4), "peak_source": tsrc,
                         "hbm_gbs_of_3Ne": round(gbs, 1), "hbm_frac": round(gbs / peak, 4), "avg_launch_ms": fms / len(ffn),
                         "share_of_step": round(fms / ms_inst, 4),
-                        "note": "tcgen05.mma kernel (TMEM accumulators, TMA-streamed weight tiles): the narrow stages are bound by HBM and by the "
-                                "epilogue warps' instruction issue (GELU), the wide ones by the latency of the weight stream from L2 (DESIGN.md 3.3)"}
+                        "note": "tcgen05.mma kernel (TMEM accumulators, TMA-streamed weight tiles, writer warps for the residual + stores): the narrow stages "
+                                "are bound by the epilogue warps' instruction issue (GELU), the wide ones by shared-memory bandwidth (SS-mode operand "
+                                "fetch + the weight stream share 128 B/clock: 48 KB per 4-MMA ring slot = 384 clocks, DESIGN.md 3.4)"}
 
     extras = {} if args.no_extras else run_extras(args, rank, world, dev, peak)
 
@@ -584,7 +585,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "variant": MODEL, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "resolution": RES,
                    "parallelism": f"replicas x{world} (no data-path collective)", "weights": "random-init",
-                   "memory_format": args.memory_format + " (NCHW planes for every kernel of this repo; the stem and stage 3 mixers are library convs)",
+                   "memory_format": args.memory_format + " (NCHW planes for every kernel of this repo: stem, RecConv, channel mixers and downsample convs of all four stages; library kernels only for the pooled head)",
                    "l2": "per-step activations (>= 100 MB per stage-0 tensor) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": x_host.numel() * 2,
