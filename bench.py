@@ -570,8 +570,8 @@ def main():
                         "hbm_gbs_of_3Ne": round(gbs, 1), "hbm_frac": round(gbs / peak, 4), "avg_launch_ms": fms / len(ffn),
                         "share_of_step": round(fms / ms_inst, 4),
                         "note": "tcgen05.mma kernel (TMEM accumulators, TMA-streamed weight tiles, writer warps for the residual + stores): the narrow stages "
-                                "are bound by the epilogue warps' instruction issue (GELU), the wide ones by shared-memory bandwidth (SS-mode operand "
-                                "fetch + the weight stream share 128 B/clock: 48 KB per 4-MMA ring slot = 384 clocks, DESIGN.md 3.4)"}
+                                "are bound by the epilogue warps' instruction issue (GELU), the wide ones by the MMA issuer's instruction chain "
+                                "(345 clocks per 4-MMA ring slot against 256 of math, DESIGN.md 3.4)"}
 
     extras = {} if args.no_extras else run_extras(args, rank, world, dev, peak)
 
