@@ -319,20 +319,22 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
         const int last_steps = p.kwLast / 16;
         uint32_t wslot = 0, wphase = 0;
         // four (or `steps`) K steps of one ring slot: D (+)= A[slot] . B
-        long long acc_wait = 0, acc_issue = 0, acc_slots = 0;
+        long long acc_wait = 0, acc_issue = 0, acc_slots = 0;   // (per-slot clock reads were removed from the hot loop: `acc_slots` only)
         const bool profiling = prof != nullptr && blockIdx.x == 0;
         // The barrier of the NEXT slot is probed (non-blocking) before this slot's MMAs are issued: the probe's ~100-clock latency
         // passes while the tensor pipe takes the MMAs, instead of in front of the next slot.
         bool have = false;                          // W_FULL of the current slot has already been observed
+        const bool solo = CS == 1;
+        const uint32_t rs_last = (uint32_t)RS - 1u;
+        uint32_t wfull = wfull0, wempty = wempty0;  // barrier addresses and A descriptor of the current slot, advanced by increments
+        uint64_t a_desc = a_ring;
         auto slot_mmas = [&](uint32_t d, uint64_t bd, bool fresh, int steps) {
-            long long c0 = 0, c1 = 0;
-            if (profiling) c0 = clock64();
-            if (!have) tc::mbar_wait(wfull0 + 8u * wslot, wphase);
+            if (!have) tc::mbar_wait(wfull, wphase);
             tc::fence_after_sync();
-            if (profiling) c1 = clock64();
-            const uint32_t nslot = wslot + 1 == (uint32_t)RS ? 0u : wslot + 1, nphase = wslot + 1 == (uint32_t)RS ? wphase ^ 1u : wphase;
-            const bool next_ready = tc::mbar_test_wait(wfull0 + 8u * nslot, nphase);
-            const uint64_t ad = a_ring + (uint64_t)(wslot * (kTileBytes / 16));
+            const bool wrap = wslot == rs_last;
+            const uint32_t nfull = wrap ? wfull0 : wfull + 8u, nphase = wrap ? wphase ^ 1u : wphase;
+            const bool next_ready = tc::mbar_test_wait(nfull, nphase);
+            const uint64_t ad = a_desc;
             if (steps == 4) {
                 if (leader) {
                     tc::mma_ss(d, ad, bd, idesc, fresh ? 0u : 1u);
@@ -345,12 +347,15 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                     if (leader) tc::mma_ss(d, ad + (uint64_t)(256 * j), bd + (uint64_t)(16 * j), idesc, (fresh && j == 0) ? 0u : 1u);
             }
             if (leader) {
-                if (CS == 1) tc::mma_commit(wempty0 + 8u * wslot);
-                else mma_commit_mcast(wempty0 + 8u * wslot, cmask);
+                if (solo) tc::mma_commit(wempty);
+                else mma_commit_mcast(wempty, cmask);
             }
-            if (profiling) { const long long c2 = clock64(); acc_wait += c1 - c0; acc_issue += c2 - c1; ++acc_slots; }
             have = next_ready;
-            wslot = nslot; wphase = nphase;
+            wfull = nfull; wphase = nphase;
+            wempty = wrap ? wempty0 : wempty + 8u;
+            a_desc = wrap ? a_ring : a_desc + (uint64_t)(kTileBytes / 16);
+            wslot = wrap ? 0u : wslot + 1u;
+            ++acc_slots;
         };
         int s = 0;                                  // chunk g = (tile of this CTA, hidden chunk s)
         uint32_t ybuf = 0, yphase = 0;              // activation buffer of chunk g's tile
