@@ -6,5 +6,7 @@ calling it does — there is no CPU fallback.
 """
 from .recattn import RecAttn2d, recattn_down_forward, recattn_up_forward  # noqa: F401
 from .recconv import RecConv2d, plan_describe, recconv_backward, recconv_forward  # noqa: F401
+from .variants import LsRecAttn2d, MllaRecConv2d, PartialChannelOperation  # noqa: F401
 
-__all__ = ["RecConv2d", "recconv_forward", "recconv_backward", "plan_describe", "RecAttn2d", "recattn_down_forward", "recattn_up_forward"]
+__all__ = ["RecConv2d", "recconv_forward", "recconv_backward", "plan_describe", "RecAttn2d", "recattn_down_forward", "recattn_up_forward",
+           "MllaRecConv2d", "LsRecAttn2d", "PartialChannelOperation"]

@@ -170,12 +170,12 @@ class _LinearAttention(nn.Module):
     ``state_dict`` are the reference's.  Inference only: there is no backward and, deliberately, no PyTorch fallback — anything the
     kernel does not serve raises."""
 
-    def __init__(self, dim, num_heads):
+    def __init__(self, dim, num_heads, conv_bias=False):
         super().__init__()
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
-        self.qk = ConvNorm(dim, dim * 2, kernel_size=1, groups=2)
-        self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim)
+        self.qk = ConvNorm(dim, dim * 2, kernel_size=1, groups=2, bias=conv_bias)   # (conv_bias: the L-series ConvNorm keeps the conv's bias,
+        self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim, bias=conv_bias)   #  lsnet/model/recattn.py:128-146)
 
     def forward(self, x):
         if self.training:
@@ -198,7 +198,7 @@ class LinearAttention2(_LinearAttention):
 class RecAttn2d(nn.Module):
     """``RecAttn2d(dim, num_heads, kernel_size=5, stage=1, mode='nearest')`` — reference model/recattn.py:54-67."""
 
-    def __init__(self, dim, num_heads, kernel_size=5, stage=1, mode="nearest"):
+    def __init__(self, dim, num_heads, kernel_size=5, stage=1, mode="nearest", conv_bias=False):
         super().__init__()
         if kernel_size != 5:
             raise ValueError("RecAttn2d: the CUDA kernels are built for kernel_size 5 (the reference's value)")
@@ -207,10 +207,10 @@ class RecAttn2d(nn.Module):
         self.mode = mode
         LinearAttention = LinearAttention2 if stage >= 3 else LinearAttention1
         self.down = nn.Sequential(
-            ConvNorm(dim, dim, kernel_size=kernel_size, padding=kernel_size // 2, stride=2, groups=dim),
-            LinearAttention(dim=dim, num_heads=num_heads),
+            ConvNorm(dim, dim, kernel_size=kernel_size, padding=kernel_size // 2, stride=2, groups=dim, bias=conv_bias),
+            LinearAttention(dim=dim, num_heads=num_heads, conv_bias=conv_bias),
         )
-        self.conv = ConvNorm(dim, dim, kernel_size=kernel_size, padding=kernel_size // 2, groups=dim)
+        self.conv = ConvNorm(dim, dim, kernel_size=kernel_size, padding=kernel_size // 2, groups=dim, bias=conv_bias)
 
     def forward(self, x):
         if self.training:
