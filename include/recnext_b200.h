@@ -104,8 +104,9 @@ RECNEXT_API int recconv_backward(const recconv_desc* d, const recconv_params* p,
 
 /*
  * RecAttn2d (A-series token mixer, reference model/recattn.py:54-67), the two plane-independent pieces around the
- * linear attention, for 16-bit activations (bf16 / fp16; k = 5; BatchNorm folded into w, b as ConvNorm.fuse does,
- * model/recattn.py:87-111).  Inference entry points: there is no backward for them yet.
+ * linear attention (BatchNorm folded into w, b as ConvNorm.fuse does, model/recattn.py:87-111).  16-bit activations with k = 5
+ * (every RecNeXt-A model under autocast) run on the tensor-core kernel; fp32 activations (the 1e-5 parity bar) and k = 3 / 7 run
+ * on a plain fp32-accumulating kernel without workspace (csrc/gstream.cu).  Inference entry points: there is no backward yet.
  *
  *   recattn_down_forward  replaces  RecAttn2d.down[0]                      model/recattn.py:60,67
  *       out[B,C,H1,W1] = depthwise k x k stride-2 conv of x[B,C,H,W] (+ b),  H1 = (H-1)/2+1, W1 = (W-1)/2+1

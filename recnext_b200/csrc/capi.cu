@@ -330,8 +330,13 @@ static int recattn_launch(const recconv_desc* d, int variant, const void* w, con
     if (d->B == 0 || d->C == 0) return RECNEXT_OK;
     if (!x || !out || !w || (variant == 2 && !z)) return fail(RECNEXT_EINVAL, "%s: null tensor", what);
     if ((d->has_bias != 0) != (b != nullptr)) return fail(RECNEXT_EINVAL, "%s: b must be given iff has_bias", what);
-    if (d->k != 5 || !(d->dtype == RECNEXT_BF16 || d->dtype == RECNEXT_F16))
-        return fail(RECNEXT_EUNSUPPORTED, "%s: built for 16-bit activations and kernel_size 5 (tensor-core path) only", what);
+    if (d->k != 5 || !(d->dtype == RECNEXT_BF16 || d->dtype == RECNEXT_F16)) {
+        // fp32 activations (the 1e-5 bar) or k = 3 / 7: the plain grid-stride kernel of gstream.cu (no workspace)
+        const GStreamDesc g = stream_desc(d);
+        const cudaError_t e = gstream_recattn(g, variant, w, b, x, z, zH, zW, out, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(RECNEXT_ECUDA, "%s(fp32): %s", what, cudaGetErrorString(e));
+        return RECNEXT_OK;
+    }
     if ((((uintptr_t)x | (uintptr_t)out | (uintptr_t)z) & 3) != 0) return fail(RECNEXT_EINVAL, "%s: tensors must be 4-byte aligned", what);
     MPlanOptions opt;
     opt.num_sms = device_sms();

@@ -320,6 +320,52 @@ cudaError_t g_run(const GStreamDesc& d, const KernelArgs& a, float* ws, bool bwd
     return cudaGetLastError();
 }
 
+
+// ---- RecAttn2d pieces for activations the tensor-core kernels do not take (fp32: the 1e-5 bar).  No workspace: the filter is read
+// from the parameter tensor, and the tail evaluates s = x + interpolate(z) at each of the K*K taps of an output on the fly
+// (correctness and coverage, not speed: 4 K*K loads of z per output in bilinear mode).
+//   variant 1: out = conv_s2(x) + b                          model/recattn.py:60 (`down[0]`, BatchNorm folded by the caller)
+//   variant 2: out = conv_s1(x + interpolate(z)) + b         model/recattn.py:67
+template <int K>
+__global__ void g_recattn(int variant, const void* __restrict__ x, const void* __restrict__ z, void* __restrict__ out, int dtype, const void* __restrict__ w,
+                          const void* __restrict__ b, int wdtype, int C, long planes, int H, int W, int zH, int zW, int Ho, int Wo, int mode) {
+    constexpr int PAD = K / 2, KK = K * K;
+    const int S = variant == 1 ? 2 : 1;
+    const long total = planes * Ho * Wo;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % Wo);
+        const long t = idx / Wo;
+        const int i = (int)(t % Ho);
+        const long p = t / Ho;
+        const int c = (int)(p % C);
+        const long xb = p * (long)H * W, zb = p * (long)zH * zW;
+        float acc = b ? rc_load_param(b, wdtype, c) : 0.f;
+        for (int r = 0; r < K; ++r) {
+            const int yy = i * S + r - PAD;
+            if (yy < 0 || yy >= H) continue;
+            for (int q = 0; q < K; ++q) {
+                const int xx = j * S + q - PAD;
+                if (xx < 0 || xx >= W) continue;
+                float v = g_load(x, dtype, xb + (long)yy * W + xx);
+                if (variant == 2) {
+                    if (mode == 1) {
+                        v += g_load(z, dtype, zb + (long)rc_nearest_src(zH, H, yy) * zW + rc_nearest_src(zW, W, xx));
+                    } else {
+                        int y0, y1, x0, x1; float ly, lx;
+                        rc_bilinear_src(zH, H, yy, y0, y1, ly);
+                        rc_bilinear_src(zW, W, xx, x0, x1, lx);
+                        const float hy = 1.f - ly, hx = 1.f - lx;
+                        v += hy * (hx * g_load(z, dtype, zb + (long)y0 * zW + x0) + lx * g_load(z, dtype, zb + (long)y0 * zW + x1)) +
+                             ly * (hx * g_load(z, dtype, zb + (long)y1 * zW + x0) + lx * g_load(z, dtype, zb + (long)y1 * zW + x1));
+                    }
+                }
+                acc = fmaf(v, rc_load_param(w, wdtype, (long)c * KK + r * K + q), acc);
+            }
+        }
+        g_store(out, dtype, idx, acc);
+    }
+}
+
 }  // namespace
 
 size_t gstream_workspace_bytes(const GStreamDesc& d, bool bwd) { return (size_t)g_layout(d, bwd).total * sizeof(float); }
@@ -332,6 +378,20 @@ cudaError_t gstream_launch(const GStreamDesc& d, const KernelArgs& a, void* ws, 
         case 7: return g_run<7>(d, a, w, bwd, gw, gb, st);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t gstream_recattn(const GStreamDesc& d, int variant, const void* w, const void* b, const void* x, const void* z, int zH, int zW, void* out,
+                            cudaStream_t st) {
+    const long planes = (long)d.B * d.C;
+    const int Ho = variant == 1 ? rc_down_size(d.H, d.K) : d.H, Wo = variant == 1 ? rc_down_size(d.W, d.K) : d.W;
+    const unsigned blocks = g_blocks(planes * Ho * Wo, d.num_sms);
+    switch (d.K) {
+        case 3: g_recattn<3><<<blocks, 256, 0, st>>>(variant, x, z, out, d.dtype, w, b, d.wdtype, d.C, planes, d.H, d.W, zH, zW, Ho, Wo, d.mode); break;
+        case 5: g_recattn<5><<<blocks, 256, 0, st>>>(variant, x, z, out, d.dtype, w, b, d.wdtype, d.C, planes, d.H, d.W, zH, zW, Ho, Wo, d.mode); break;
+        case 7: g_recattn<7><<<blocks, 256, 0, st>>>(variant, x, z, out, d.dtype, w, b, d.wdtype, d.C, planes, d.H, d.W, zH, zW, Ho, Wo, d.mode); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
 }
 
 }  // namespace recnext

@@ -35,8 +35,8 @@ def _call_desc(x: torch.Tensor, mode: str, wdtype: torch.dtype, has_bias: bool) 
         raise ValueError(f"RecAttn2d expects [B,C,H,W], got {tuple(x.shape)}")
     if not x.is_cuda:
         raise RuntimeError("recnext_b200.RecAttn2d runs on CUDA (sm_100a) only; there is no CPU fallback")
-    if x.dtype not in (torch.bfloat16, torch.float16):
-        raise TypeError(f"RecAttn2d kernels are built for 16-bit activations (bfloat16 / float16), got {x.dtype}")
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"RecAttn2d: float32 / bfloat16 / float16 activations only, got {x.dtype}")   # 16-bit: tensor-core kernels; fp32: the 1e-5 path
     B, C, H, W = x.shape
     return N.RecConvDesc(B, C, H, W, 5, 1, _MODES[mode], _DTYPES[x.dtype], _DTYPES[wdtype], int(has_bias))
 

@@ -99,6 +99,27 @@ def test_cuda_pieces_against_reference(path, dtype):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
+def test_cuda_fp32_pieces_and_module_at_1e5(path):
+    """fp32 bar of the north star (1e-5) for RecAttn2d (model/recattn.py:54-67): the two pieces on the fp32 kernels of gstream.cu and the whole
+    eval-mode module (fp32 linear-attention kernel in between), against outputs of the unmodified reference"""
+    from recnext_b200.recattn import recattn_down_forward, recattn_up_forward
+
+    z, meta, sd = _load(path)
+    m = _module(meta, sd).cuda()
+    x = torch.from_numpy(z["x"]).cuda()
+    wd, bd = m.down[0].folded()
+    low = recattn_down_forward(x, wd, bd)
+    assert low.dtype == torch.float32 and rel_err(low.cpu().numpy(), z["low"]) < 1e-5
+    wc, bc = m.conv.folded()
+    y = recattn_up_forward(x, torch.from_numpy(z["z"]).cuda(), wc, bc, meta["mode"])
+    assert rel_err(y.cpu().numpy(), z["y"]) < 1e-5
+    with torch.no_grad():
+        ym = m(x)
+    assert ym.dtype == torch.float32 and rel_err(ym.cpu().numpy(), z["y"]) < 2e-5   # (the qk / pe ConvNorms are cuDNN fp32 convs: TF32 off in conftest)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
 def test_cuda_module_against_reference(path):
     z, meta, sd = _load(path)
     m = _module(meta, sd).cuda()
