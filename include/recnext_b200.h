@@ -185,6 +185,13 @@ RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t 
  */
 RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* qk, const void* v,
                                         const void* pe, void* out, void* stream);
+/*
+ * The same contraction with q and k as two [B, dim, n] tensors (the pre-activation outputs of the two halves of the grouped 1x1 `qk`
+ * conv, e.g. written by two batched GEMMs) and optional fp32 per-channel biases [dim] that are added before the elu — so the caller's
+ * GEMM needs no bias pass.  model/recattn.py:13,21 (`qk`), :21-28.
+ */
+RECNEXT_API int recnext_linattn_forward_qk(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* q, const void* k,
+                                           const float* qbias, const float* kbias, const void* v, const void* pe, void* out, void* stream);
 
 /* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);

@@ -23,7 +23,8 @@ cudaError_t mb_launch(const MBPlan&, const KernelArgs&, float* gw, float* gb, cu
 bool m_static_geometry(const MPlan&);
 struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ, staged, offW, kc; };  // ffn_mma.cu
 int ffn_make_plan(FfnPlan&, int B, int C, int HID, int HW, int dtype);
-int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* qk, const void* v, const void* pe, void* out, cudaStream_t stream, cudaError_t* err);
+int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe,
+                   void* out, cudaStream_t stream, cudaError_t* err);
 int dwdown_launch(int B, int C, int H, int W, int dtype, const void* x, const float* w, const float* b, void* out, cudaStream_t stream, cudaError_t* err);
 cudaError_t ffn_launch(const FfnPlan&, const void* y, const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
                        cudaStream_t stream);
@@ -366,16 +367,28 @@ RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const v
     return recattn_launch(d, 2, w, b, x, z, zH, zW, y, stream, "recattn_up_forward");
 }
 
+static int linattn_call(const char* what, int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* q, const void* k, const float* qb,
+                        const float* kb, const void* v, const void* pe, void* out, void* stream) {
+    if (B < 0 || dim < 1 || heads < 1 || n < 1) return fail(RECNEXT_EINVAL, "%s: bad shape [%d,%d,%d] heads %d", what, B, dim, n, heads);
+    if (B == 0) return RECNEXT_OK;
+    if (!q || !k || !v || !out) return fail(RECNEXT_EINVAL, "%s: null tensor", what);
+    cudaError_t e = cudaSuccess;
+    const int rc = linattn_launch(B, dim, heads, n, dtype, q, k, qb, kb, v, pe, out, (cudaStream_t)stream, &e);
+    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "%s: head_dim in {4,8,16,20,24,28,32,40} only (dim %d, heads %d)", what, dim, heads);
+    if (rc) return fail(RECNEXT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    return RECNEXT_OK;
+}
+
 RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* qk, const void* v, const void* pe,
                             void* out, void* stream) {
-    if (B < 0 || dim < 1 || heads < 1 || n < 1) return fail(RECNEXT_EINVAL, "recnext_linattn_forward: bad shape [%d,%d,%d] heads %d", B, dim, n, heads);
-    if (B == 0) return RECNEXT_OK;
-    if (!qk || !v || !out) return fail(RECNEXT_EINVAL, "recnext_linattn_forward: null tensor");
-    cudaError_t e = cudaSuccess;
-    const int rc = linattn_launch(B, dim, heads, n, dtype, qk, v, pe, out, (cudaStream_t)stream, &e);
-    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_linattn_forward: head_dim in {4,8,16,20,24,28,32,40} only (dim %d, heads %d)", dim, heads);
-    if (rc) return fail(RECNEXT_ECUDA, "recnext_linattn_forward: %s", cudaGetErrorString(e));
-    return RECNEXT_OK;
+    const size_t esz = dtype == RECNEXT_F32 ? 4 : 2;
+    const void* k = qk ? (const void*)((const char*)qk + (size_t)dim * (size_t)n * esz) : nullptr;
+    return linattn_call("recnext_linattn_forward", B, dim, heads, n, dtype, qk, k, nullptr, nullptr, v, pe, out, stream);
+}
+
+RECNEXT_API int recnext_linattn_forward_qk(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* q, const void* k, const float* qbias,
+                               const float* kbias, const void* v, const void* pe, void* out, void* stream) {
+    return linattn_call("recnext_linattn_forward_qk", B, dim, heads, n, dtype, q, k, qbias, kbias, v, pe, out, stream);
 }
 
 RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w, const float* b,

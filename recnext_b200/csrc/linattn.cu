@@ -30,7 +30,8 @@ template <> __device__ __forceinline__ float la_from_f<float>(float v) { return 
 __device__ __forceinline__ float la_elu1(float v) { return v > 0.f ? v + 1.f : expf(v); }   // elu(v) + 1 (expm1(v) + 1 = exp(v))
 
 template <typename T, int D>
-__global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __restrict__ qk, const T* __restrict__ v, const T* __restrict__ pe,
+__global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __restrict__ q_pre, const T* __restrict__ k_pre, const float* __restrict__ qbias,
+                                                                 const float* __restrict__ kbias, const T* __restrict__ v, const T* __restrict__ pe,
                                                                  T* __restrict__ out, int heads, int n) {
     constexpr int TQ = (D + 3) / 4;            // 4 x 4 register tiles per kv dimension
     constexpr int DP = TQ * 4;                 // padded d
@@ -44,8 +45,13 @@ __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __rest
     const int tid = threadIdx.x;
     const int b = blockIdx.x / heads, h = blockIdx.x - b * heads;
     const int dim = heads * D;
-    const T* qp = qk + ((long)b * 2 * dim + h * D) * n;            // q rows i: qp + i * n
-    const T* kp = qp + (long)dim * n;
+    // q / k rows i of this head: base + i * n.  The two tensors are [B, dim, n] each (one [B, 2 dim, n] tensor when the caller's `qk`
+    // ConvNorm wrote them together: then k_pre = q_pre + dim * n and the image stride is 2 dim n); optional per-channel biases.
+    const long img = (k_pre == q_pre + (long)dim * n) ? 2l * dim * n : (long)dim * n;
+    const T* qp = q_pre + (long)b * img + (long)h * D * n;
+    const T* kp = k_pre + (long)b * img + (long)h * D * n;
+    const float* qbp = qbias ? qbias + h * D : nullptr;
+    const float* kbp = kbias ? kbias + h * D : nullptr;
     const T* vp = v + ((long)b * dim + h * D) * n;
     const float inv_n = 1.f / (float)n;
     for (int i = tid; i < (DP - D) * (CH + 1); i += 256) { ks[D + i / (CH + 1)][i % (CH + 1)] = 0.f; vs[D + i / (CH + 1)][i % (CH + 1)] = 0.f; }
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __rest
         for (int i = tid; i < D * CH; i += 256) {
             const int row = i / CH, px = i - row * CH;     // consecutive threads read consecutive pixels of one channel row
             float kk = 0.f, vv = 0.f;
-            if (px < cn) { kk = la_elu1(la_to_f<T>(kp[(long)row * n + c0 + px])); vv = la_to_f<T>(vp[(long)row * n + c0 + px]); }
+            if (px < cn) { kk = la_elu1(la_to_f<T>(kp[(long)row * n + c0 + px]) + (kbp ? kbp[row] : 0.f)); vv = la_to_f<T>(vp[(long)row * n + c0 + px]); }
             ks[row][px] = kk; vs[row][px] = vv;
         }
         __syncthreads();
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __rest
         const int cn = (n - c0) < CH ? (n - c0) : CH;
         for (int i = tid; i < D * CH; i += 256) {
             const int row = i / CH, px = i - row * CH;
-            ks[row][px] = px < cn ? la_elu1(la_to_f<T>(qp[(long)row * n + c0 + px])) : 0.f;
+            ks[row][px] = px < cn ? la_elu1(la_to_f<T>(qp[(long)row * n + c0 + px]) + (qbp ? qbp[row] : 0.f)) : 0.f;
         }
         __syncthreads();
         if (tid < CH) {
@@ -150,9 +156,10 @@ __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __rest
 }
 
 template <typename T>
-static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* qk, const void* v, const void* pe, void* out, cudaStream_t s) {
+static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe, void* out,
+                               cudaStream_t s) {
     const int grid = B * heads;
-#define LA_CASE(DD) case DD: recnext_linattn_kernel<T, DD><<<grid, 256, 0, s>>>((const T*)qk, (const T*)v, (const T*)pe, (T*)out, heads, n); break;
+#define LA_CASE(DD) case DD: recnext_linattn_kernel<T, DD><<<grid, 256, 0, s>>>((const T*)q, (const T*)k, qb, kb, (const T*)v, (const T*)pe, (T*)out, heads, n); break;
     switch (d) {
         LA_CASE(4) LA_CASE(8) LA_CASE(16) LA_CASE(20) LA_CASE(24) LA_CASE(28) LA_CASE(32) LA_CASE(40)
         default: return cudaErrorInvalidValue;
@@ -162,12 +169,15 @@ static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* qk, c
 }
 
 // 0 ok, 1 unsupported head_dim / dtype, 2 CUDA error in *err
-int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* qk, const void* v, const void* pe, void* out, cudaStream_t stream, cudaError_t* err) {
+// q, k: [B, dim, n] each (k == q + dim * n elements: one [B, 2 dim, n] tensor); qb / kb: fp32 [dim] biases added before the elu, or null
+int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe,
+                   void* out, cudaStream_t stream, cudaError_t* err) {
     if (heads < 1 || dim % heads != 0 || dtype < 0 || dtype > 2) return 1;
     const int d = dim / heads;
     if (!(d == 4 || d == 8 || d == 16 || d == 20 || d == 24 || d == 28 || d == 32 || d == 40)) return 1;
-    *err = dtype == 0 ? la_launch_t<float>(B, heads, d, n, qk, v, pe, out, stream)
-         : dtype == 1 ? la_launch_t<__nv_bfloat16>(B, heads, d, n, qk, v, pe, out, stream) : la_launch_t<__half>(B, heads, d, n, qk, v, pe, out, stream);
+    *err = dtype == 0 ? la_launch_t<float>(B, heads, d, n, q, k, qb, kb, v, pe, out, stream)
+         : dtype == 1 ? la_launch_t<__nv_bfloat16>(B, heads, d, n, q, k, qb, kb, v, pe, out, stream)
+                      : la_launch_t<__half>(B, heads, d, n, q, k, qb, kb, v, pe, out, stream);
     return *err == cudaSuccess ? 0 : 2;
 }
 

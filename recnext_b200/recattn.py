@@ -20,6 +20,7 @@ not have — there is no PyTorch fallback anywhere in this file (the eager resta
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -159,7 +160,35 @@ def linattn_forward(qk: torch.Tensor, v: torch.Tensor, pe: Optional[torch.Tensor
     return out
 
 
+def linattn_forward_qk(q: torch.Tensor, k: torch.Tensor, qbias: Optional[torch.Tensor], kbias: Optional[torch.Tensor], v: torch.Tensor,
+                       pe: Optional[torch.Tensor], num_heads: int) -> torch.Tensor:
+    """``linattn_forward`` with q and k as two [B, dim, h, w] (or [B, dim, n]) pre-activation tensors and optional fp32 biases [dim] that the
+    kernel adds before the elu (``recnext_linattn_forward_qk``): the caller's GEMMs need no bias pass."""
+    if not v.is_cuda:
+        raise RuntimeError("recnext_b200.linattn_forward_qk runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if v.dtype not in _DTYPES:
+        raise TypeError(f"linattn_forward_qk: float32 / bfloat16 / float16 only, got {v.dtype}")
+    v = v.contiguous()
+    q, k = q.to(v.dtype).contiguous(), k.to(v.dtype).contiguous()
+    pe = None if pe is None else pe.to(v.dtype).contiguous()
+    B, dim, H, W = v.shape
+    if q.numel() != v.numel() or k.numel() != v.numel():
+        raise ValueError(f"linattn_forward_qk: q {tuple(q.shape)} / k {tuple(k.shape)} do not match v {tuple(v.shape)}")
+    qb = None if qbias is None else qbias.detach().float().contiguous()
+    kb = None if kbias is None else kbias.detach().float().contiguous()
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        ev = _timing_start()
+        N.check(N.lib().recnext_linattn_forward_qk(B, dim, num_heads, H * W, _DTYPES[v.dtype], q.data_ptr(), k.data_ptr(),
+                                                   None if qb is None else qb.data_ptr(), None if kb is None else kb.data_ptr(), v.data_ptr(),
+                                                   None if pe is None else pe.data_ptr(), out.data_ptr(), _stream(v)), "recnext_linattn_forward_qk")
+        _timing_stop(ev, (4 * v.numel() + (0 if pe is None else pe.numel())) * v.element_size(), ("linattn",) + tuple(v.shape))
+    return out
+
+
 LINATTN_HEAD_DIMS = (4, 8, 16, 20, 24, 28, 32, 40)   # 20..40: the RecNeXt-A models; 4, 8, 16: small test models
+# RECNEXT_LINATTN_GEMM=0: the grouped 1x1 `qk` ConvNorm runs as the library's grouped conv (round-2 path; A/B measurements)
+LINATTN_GEMM = os.environ.get("RECNEXT_LINATTN_GEMM", "1") != "0"
 
 
 class _LinearAttention(nn.Module):
@@ -167,8 +196,10 @@ class _LinearAttention(nn.Module):
     d x d ``kv`` form, stages 0-2) and LinearAttention2 (:31-51, the n x n form, stage 3, n = 16) — and checks that the two agree
     (lsnet/model/recattn.py:480-501); both are served by ONE kernel that always takes the d x d route (``recnext_linattn_forward``):
     q, k = elu(qk(x)) + 1;  out = q^T (k v^T / n) / (q^T mean(k) + 1e-6) + pe(x).  Sub-module names (``qk``, ``pe``) and therefore the
-    ``state_dict`` are the reference's.  Inference only: there is no backward and, deliberately, no PyTorch fallback — anything the
-    kernel does not serve raises."""
+    ``state_dict`` are the reference's.  The grouped (groups = 2) 1x1 ``qk`` ConvNorm is two plain GEMMs per image, W_q x[: dim/2] and
+    W_k x[dim/2 :]: the library's grouped-conv kernels for it are SGEMM-class (15 % of an A3 step with their bias adds), so it runs as two
+    batched tensor-core GEMMs (``torch.bmm`` on the BatchNorm-folded weights, cuBLAS) whose bias the attention kernel adds before the elu.
+    Inference only: there is no backward and, deliberately, no PyTorch fallback — anything the kernel does not serve raises."""
 
     def __init__(self, dim, num_heads, conv_bias=False):
         super().__init__()
@@ -176,6 +207,21 @@ class _LinearAttention(nn.Module):
         self.head_dim = dim // num_heads
         self.qk = ConvNorm(dim, dim * 2, kernel_size=1, groups=2, bias=conv_bias)   # (conv_bias: the L-series ConvNorm keeps the conv's bias,
         self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim, bias=conv_bias)   #  lsnet/model/recattn.py:128-146)
+        self._qk_cache = None
+
+    def _qk_params(self, dtype, device):
+        """BatchNorm-folded `qk` weights as [2, dim, dim / 2] in the activation dtype and the fp32 bias [2 dim]; cached, keyed on the version
+        counters of the source tensors (load_state_dict / in-place updates invalidate it)."""
+        m = self.qk
+        src = [m.conv.weight, m.conv.bias, m.norm.weight, m.norm.bias, m.norm.running_mean, m.norm.running_var] if isinstance(m, ConvNorm) else [m.weight, m.bias]
+        key = (dtype, device) + tuple((id(t), t._version) for t in src if t is not None)
+        c = self._qk_cache
+        if c is None or c[0] != key:
+            w, b = _wb(m)
+            dim = w.shape[0] // 2
+            c = (key, w.detach().reshape(2, dim, dim // 2).to(dtype).contiguous(), b.detach().float().contiguous())
+            self._qk_cache = c
+        return c[1], c[2]
 
     def forward(self, x):
         if self.training:
@@ -184,7 +230,17 @@ class _LinearAttention(nn.Module):
             raise RuntimeError("recnext_b200 linear attention runs on CUDA (sm_100a) only; there is no CPU fallback")
         if self.head_dim not in LINATTN_HEAD_DIMS:
             raise RuntimeError(f"recnext_b200 linear attention: head_dim {self.head_dim} is not built (have {LINATTN_HEAD_DIMS})")
-        return linattn_forward(self.qk(x), x, self.pe(x), self.num_heads)
+        if torch.is_autocast_enabled():
+            x = x.to(torch.get_autocast_dtype("cuda"))          # (what the convs of the library path do to their input under autocast)
+        if not LINATTN_GEMM or x.dtype not in _DTYPES:
+            return linattn_forward(self.qk(x), x, self.pe(x), self.num_heads)
+        x = x.contiguous()
+        B, dim, H, W = x.shape
+        w, b = self._qk_params(x.dtype, x.device)
+        xg = x.view(B, 2, dim // 2, H * W)
+        q = torch.bmm(w[0].expand(B, dim, dim // 2), xg[:, 0])     # [B, dim, n]: batched GEMMs with the weight broadcast over the batch (stride 0)
+        k = torch.bmm(w[1].expand(B, dim, dim // 2), xg[:, 1])
+        return linattn_forward_qk(q, k, b[:dim], b[dim:], x, self.pe(x), self.num_heads)
 
 
 class LinearAttention1(_LinearAttention):
