@@ -30,7 +30,8 @@ namespace {
 constexpr int kTile = 8;                 // output pixels per tile edge
 constexpr int kMid = 2 * kTile + 1;      // 17: intermediate pixels per tile edge
 constexpr int kIn = 2 * kMid + 1;        // 35: input pixels per tile edge
-constexpr int kInPitch = 36;             // elements per input row in shared memory
+constexpr int kInPitch = 40;             // elements per input row in shared memory: the patch row sits at columns 1 .. 35 (the window that starts one
+                                         // column to its left is 8-byte aligned in global memory: 10 cp.async pieces of 4 pixels per row)
 constexpr int kHalf = (kMid + 1) / 2;    // 9: columns of one parity plane of the intermediate tile
 
 template <typename T> struct H16;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(KS == 2 ? 256 : 320, KS == 2 ? 3 : 2) recnext_
         for (int j = 0; j < 4; ++j) {
             const int k = ks * 16 + 2 * t4 + (j & 1) + 8 * (j >> 1);
             const int ci = k / 9, r = k - 9 * ci;
-            koff[ks][j] = k < 27 ? ci * (kIn * kInPitch) + (r / 3) * kInPitch + (r % 3) : 0;
+            koff[ks][j] = k < 27 ? ci * (kIn * kInPitch) + (r / 3) * kInPitch + (r % 3) + 1 : 1;
         }
 
     const int tiles_x = (W2 + kTile - 1) / kTile, tiles_y = (H2 + kTile - 1) / kTile;
@@ -127,20 +128,31 @@ __global__ void __launch_bounds__(KS == 2 ? 256 : 320, KS == 2 ? 3 : 2) recnext_
     const bool prof = p.dbg && blockIdx.x == 0;
     long long c_prev = prof ? clock64() : 0;
     auto mark = [&](int i) { if (prof) { const long long c = clock64(); ph[i] += c - c_prev; c_prev = c; } };
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // The patch of a tile: rows [4 oy0 - 3, + 35) x columns [4 ox0 - 3, + 35) of the three input planes, zero outside the image.  Aligned images
+    // (W % 4 == 0, 8-byte aligned base) take it by 8-byte cp.async -- issued for the NEXT tile as soon as conv1 has read this one, so the copies
+    // land under conv2; anything else is loaded element-wise.
+    const bool aligned = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+    const uint32_t s_in32 = sb;
+    auto load_patch = [&](long tile) {
         const int b = (int)(tile / (tiles_y * tiles_x));
         const int tr = (int)(tile - (long)b * tiles_y * tiles_x);
-        const int oy0 = (tr / tiles_x) * kTile, ox0 = (tr % tiles_x) * kTile;
-        const int y1_0 = 2 * oy0 - 1, x1_0 = 2 * ox0 - 1;           // intermediate coordinates of the tile's first row / column
-        __syncthreads();   // the previous tile's conv2 has read the intermediate tile; (first pass) the weight image is written
-        mark(0);
-        // ---- 1. input patch: a warp per patch row, lanes along x (35 = 32 + 3 elements), four rows in flight per warp
-        {
-            const int yi_0 = 2 * y1_0 - 1, xi_0 = 2 * x1_0 - 1;     // input coordinates of the patch's first row / column
-            const unsigned short* xb = reinterpret_cast<const unsigned short*>(x) + (size_t)b * 3 * H * W;
+        const int yi_0 = 4 * (tr / tiles_x) * kTile - 3, xi_0 = 4 * (tr % tiles_x) * kTile - 3;
+        const unsigned short* xb = reinterpret_cast<const unsigned short*>(x) + (size_t)b * 3 * H * W;
+        if (aligned) {
+            const int xw0 = xi_0 - 1;                         // multiple of 4
+            for (int i = tid; i < 3 * kIn * 10; i += blockDim.x) {
+                const int r = i / 10, pc = i - r * 10;
+                const int ci = r / kIn, iy = r - ci * kIn, yy = yi_0 + iy, xx = xw0 + 4 * pc;
+                const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;      // (a piece is entirely inside or outside: the edges are multiples of 4)
+                const unsigned short* src = ok ? xb + ((size_t)ci * H + yy) * W + xx : xb;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s_in32 + (uint32_t)((ci * (kIn * kInPitch) + iy * kInPitch + 4 * pc) * 2)), "l"(src),
+                             "r"(ok ? 8 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
             const int xa = xi_0 + lane, xc = xa + 32;
             const bool oka = xa >= 0 && xa < W, okc = lane < kIn - 32 && xc >= 0 && xc < W;
-            for (int r0 = warp; r0 < 3 * kIn; r0 += 4 * nwarps) {
+            for (int r0 = warp; r0 < 3 * kIn; r0 += 4 * nwarps) {   // a warp per patch row, lanes along x, four rows in flight per warp
                 unsigned short va[4], vc[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -156,18 +168,29 @@ __global__ void __launch_bounds__(KS == 2 ? 256 : 320, KS == 2 ? 3 : 2) recnext_
                     const int r = r0 + j * nwarps;
                     if (r < 3 * kIn) {
                         const int ci = r / kIn, iy = r - ci * kIn;
-                        unsigned short* dst = s_in + ci * (kIn * kInPitch) + iy * kInPitch;
+                        unsigned short* dst = s_in + ci * (kIn * kInPitch) + iy * kInPitch + 1;
                         dst[lane] = va[j];
                         if (lane < kIn - 32) dst[lane + 32] = vc[j];
                     }
                 }
             }
         }
-        __syncthreads();
+    };
+    __syncthreads();   // the weight image is written
+    if ((long)blockIdx.x < ntiles) load_patch(blockIdx.x);
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = (int)(tile / (tiles_y * tiles_x));
+        const int tr = (int)(tile - (long)b * tiles_y * tiles_x);
+        const int oy0 = (tr / tiles_x) * kTile, ox0 = (tr % tiles_x) * kTile;
+        const int y1_0 = 2 * oy0 - 1, x1_0 = 2 * ox0 - 1;           // intermediate coordinates of the tile's first row / column
+        mark(0);
+        // ---- 1. this tile's patch has been requested (before the loop, or under the previous tile's conv2)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();   // ... and is visible to every warp; the previous tile's conv2 has read the intermediate tile
         mark(1);
         mark(2);
         // ---- 2. conv1 + GELU -> intermediate tile
-        for (int mt = warp; mt < (kMid * kMid + 15) / 16; mt += nwarps) {
+        for (int mt = warp; mt < (kMid * kMid + 15) / 16; mt += nwarps) {   // (half-tile work items balance the warps better but pay the A gather twice: slower)
             int base[2], py[2], px[2];
             bool live[2];
 #pragma unroll
@@ -210,8 +233,9 @@ __global__ void __launch_bounds__(KS == 2 ? 256 : 320, KS == 2 ? 3 : 2) recnext_
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // conv1 is done with the patch and the intermediate tile is complete
         mark(3);
+        if (tile + gridDim.x < ntiles) load_patch(tile + gridDim.x);   // the next tile's patch lands under conv2
         // ---- 3. conv2: warp = (pair of n-tiles, half of the m-tiles)
         {
             const int np = warp >> 1, mh = warp & 1;       // n-tiles 2 np, 2 np + 1; m-tiles 2 mh, 2 mh + 1 (m-tile = two output rows)
