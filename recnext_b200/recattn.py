@@ -186,6 +186,13 @@ def linattn_forward_qk(q: torch.Tensor, k: torch.Tensor, qbias: Optional[torch.T
     return out
 
 
+def _no_grad_wanted(x, module, what):
+    """The A-series kernels have no backward: refuse to cut a gradient silently (an eval-mode model stays differentiable in the reference)."""
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+        raise RuntimeError(f"recnext_b200 {what}: the sm_100a kernels have no backward and a gradient can be asked for here (grad mode is on and the "
+                           "input or a parameter requires grad) — run under torch.no_grad() / inference_mode(), or freeze the parameters")
+
+
 LINATTN_HEAD_DIMS = (4, 8, 16, 20, 24, 28, 32, 40)   # 20..40: the RecNeXt-A models; 4, 8, 16: small test models
 # RECNEXT_LINATTN_GEMM=0: the grouped 1x1 `qk` ConvNorm runs as the library's grouped conv (round-2 path; A/B measurements)
 LINATTN_GEMM = os.environ.get("RECNEXT_LINATTN_GEMM", "1") != "0"
@@ -230,6 +237,7 @@ class _LinearAttention(nn.Module):
             raise RuntimeError("recnext_b200 linear attention runs on CUDA (sm_100a) only; there is no CPU fallback")
         if self.head_dim not in LINATTN_HEAD_DIMS:
             raise RuntimeError(f"recnext_b200 linear attention: head_dim {self.head_dim} is not built (have {LINATTN_HEAD_DIMS})")
+        _no_grad_wanted(x, self, "linear attention")
         if torch.is_autocast_enabled():
             x = x.to(torch.get_autocast_dtype("cuda"))          # (what the convs of the library path do to their input under autocast)
         if not LINATTN_GEMM or x.dtype not in _DTYPES:
@@ -272,6 +280,7 @@ class RecAttn2d(nn.Module):
         if self.training:
             raise RuntimeError("recnext_b200.RecAttn2d: the sm_100a kernels have no backward yet — call .eval() "
                                "(inference with BatchNorm folded); there is deliberately no PyTorch fallback")
+        _no_grad_wanted(x, self, "RecAttn2d")
         if torch.is_autocast_enabled() and x.is_cuda:
             x = x.to(torch.get_autocast_dtype("cuda"))
         wd, bd = _wb(self.down[0])

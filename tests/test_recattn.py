@@ -74,7 +74,9 @@ def test_no_fallbacks():
     m = RecAttn2d(8, 2)
     with pytest.raises(RuntimeError, match="no backward"):
         m(torch.randn(1, 8, 8, 8))
-    with pytest.raises(RuntimeError, match="CUDA"):
+    with pytest.raises(RuntimeError, match="no backward"):      # eval mode but a gradient can be asked for: no silent gradient cut
+        m.eval()(torch.randn(1, 8, 8, 8))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
         m.eval()(torch.randn(1, 8, 8, 8))
 
 

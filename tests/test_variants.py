@@ -73,7 +73,7 @@ def test_lsnet_partial_state_dict_cpu(path):
     m = PartialChannelOperation(C, LsRecAttn2d(C // 4, num_heads=heads, stage=stage), split_rate=4)
     m.load_state_dict(_sd(d), strict=True)                           # same module tree and keys as the reference
     m.eval()
-    with pytest.raises(RuntimeError, match="CUDA"):
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
         m(torch.from_numpy(d["x"]))                                  # no CPU fallback
 
 
