@@ -192,6 +192,14 @@ RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, i
  */
 RECNEXT_API int recnext_linattn_forward_qk(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* q, const void* k,
                                            const float* qbias, const float* kbias, const void* v, const void* pe, void* out, void* stream);
+/*
+ * ... and with the positional-encoding ConvNorm `pe` (depthwise 3x3, pad 1, BatchNorm folded: pe_w [dim, 9] fp32, pe_b [dim] fp32 or
+ * NULL) evaluated on v inside the kernel instead of read as a tensor: everything of LinearAttention1/2.forward after the `qk` GEMMs
+ * (model/recattn.py:14,21-28).  v / out: [B, dim, H, W].
+ */
+RECNEXT_API int recnext_linattn_forward_pe(int32_t B, int32_t dim, int32_t heads, int32_t H, int32_t W, int32_t dtype, const void* q, const void* k,
+                                           const float* qbias, const float* kbias, const void* v, const float* pe_w, const float* pe_b, void* out,
+                                           void* stream);
 
 /* Writes a one-line description of the launch plan (tiling, shared memory, grid) for logs/benchmarks. */
 RECNEXT_API int recconv_plan_describe(const recconv_desc* d, int backward, char* buf, size_t buflen);

@@ -79,6 +79,8 @@ def lib() -> ctypes.CDLL:
     L.recnext_linattn_forward.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 5
     L.recnext_linattn_forward_qk.restype = ctypes.c_int
     L.recnext_linattn_forward_qk.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 8
+    L.recnext_linattn_forward_pe.restype = ctypes.c_int
+    L.recnext_linattn_forward_pe.argtypes = [ctypes.c_int32] * 6 + [ctypes.c_void_p] * 9
     L.recnext_stem_forward.restype = ctypes.c_int
     L.recnext_stem_forward.argtypes = [ctypes.c_int32] * 6 + [ctypes.c_void_p] * 7
     L.recnext_dwdown_forward.restype = ctypes.c_int
@@ -104,5 +106,5 @@ def check(rc: int, what: str) -> None:
 EXPORTS = [
     "recnext_abi_version", "recnext_last_error", "recconv_forward", "recconv_forward_workspace_bytes", "recconv_forward_ws",
     "recconv_backward_workspace_bytes", "recconv_backward",
-    "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward", "recnext_ffn_forward", "recnext_ffn_packed_bytes", "recnext_ffn_pack", "recnext_ffn_forward_packed", "recnext_dwdown_forward", "recnext_stem_forward", "recnext_linattn_forward", "recnext_linattn_forward_qk",
+    "recconv_plan_describe", "recconv_source_index", "recattn_down_forward", "recattn_up_forward", "recnext_ffn_forward", "recnext_ffn_packed_bytes", "recnext_ffn_pack", "recnext_ffn_forward_packed", "recnext_dwdown_forward", "recnext_stem_forward", "recnext_linattn_forward", "recnext_linattn_forward_qk", "recnext_linattn_forward_pe",
 ]

@@ -24,7 +24,7 @@ bool m_static_geometry(const MPlan&);
 struct FfnPlan { int B, C, HID, HW, NTN, tiles, chunkB, PB, offX, offH, smem_bytes, dtype, NQ, staged, offW, kc; };  // ffn_mma.cu
 int ffn_make_plan(FfnPlan&, int B, int C, int HID, int HW, int dtype);
 int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe,
-                   void* out, cudaStream_t stream, cudaError_t* err);
+                   const float* pew, const float* peb, int pw, void* out, cudaStream_t stream, cudaError_t* err);
 int dwdown_launch(int B, int C, int H, int W, int dtype, const void* x, const float* w, const float* b, void* out, cudaStream_t stream, cudaError_t* err);
 cudaError_t ffn_launch(const FfnPlan&, const void* y, const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out,
                        cudaStream_t stream);
@@ -368,13 +368,14 @@ RECNEXT_API int recattn_up_forward(const recconv_desc* d, const void* w, const v
 }
 
 static int linattn_call(const char* what, int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* q, const void* k, const float* qb,
-                        const float* kb, const void* v, const void* pe, void* out, void* stream) {
+                        const float* kb, const void* v, const void* pe, void* out, void* stream, const float* pew = nullptr, const float* peb = nullptr,
+                        int32_t pw = 0) {
     if (B < 0 || dim < 1 || heads < 1 || n < 1) return fail(RECNEXT_EINVAL, "%s: bad shape [%d,%d,%d] heads %d", what, B, dim, n, heads);
     if (B == 0) return RECNEXT_OK;
     if (!q || !k || !v || !out) return fail(RECNEXT_EINVAL, "%s: null tensor", what);
     cudaError_t e = cudaSuccess;
-    const int rc = linattn_launch(B, dim, heads, n, dtype, q, k, qb, kb, v, pe, out, (cudaStream_t)stream, &e);
-    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "%s: head_dim in {4,8,16,20,24,28,32,40} only (dim %d, heads %d)", what, dim, heads);
+    const int rc = linattn_launch(B, dim, heads, n, dtype, q, k, qb, kb, v, pe, pew, peb, pw, out, (cudaStream_t)stream, &e);
+    if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "%s: head_dim in {4,8,16,20,24,28,32,40} only (dim %d, heads %d); n must be a multiple of the plane width", what, dim, heads);
     if (rc) return fail(RECNEXT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
     return RECNEXT_OK;
 }
@@ -389,6 +390,12 @@ RECNEXT_API int recnext_linattn_forward(int32_t B, int32_t dim, int32_t heads, i
 RECNEXT_API int recnext_linattn_forward_qk(int32_t B, int32_t dim, int32_t heads, int32_t n, int32_t dtype, const void* q, const void* k, const float* qbias,
                                const float* kbias, const void* v, const void* pe, void* out, void* stream) {
     return linattn_call("recnext_linattn_forward_qk", B, dim, heads, n, dtype, q, k, qbias, kbias, v, pe, out, stream);
+}
+
+RECNEXT_API int recnext_linattn_forward_pe(int32_t B, int32_t dim, int32_t heads, int32_t H, int32_t W, int32_t dtype, const void* q, const void* k,
+                               const float* qbias, const float* kbias, const void* v, const float* pe_w, const float* pe_b, void* out, void* stream) {
+    if (H < 1 || W < 1 || !pe_w) return fail(RECNEXT_EINVAL, "recnext_linattn_forward_pe: bad plane %dx%d or null pe_w", H, W);
+    return linattn_call("recnext_linattn_forward_pe", B, dim, heads, H * W, dtype, q, k, qbias, kbias, v, nullptr, out, stream, pe_w, pe_b, W);
 }
 
 RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w, const float* b,

@@ -32,6 +32,7 @@ __device__ __forceinline__ float la_elu1(float v) { return v > 0.f ? v + 1.f : e
 template <typename T, int D>
 __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __restrict__ q_pre, const T* __restrict__ k_pre, const float* __restrict__ qbias,
                                                                  const float* __restrict__ kbias, const T* __restrict__ v, const T* __restrict__ pe,
+                                                                 const float* __restrict__ pew, const float* __restrict__ peb, int pw,
                                                                  T* __restrict__ out, int heads, int n) {
     constexpr int TQ = (D + 3) / 4;            // 4 x 4 register tiles per kv dimension
     constexpr int DP = TQ * 4;                 // padded d
@@ -147,6 +148,23 @@ __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __rest
                 if (j < D) {
                     float val = o[c];
                     if (pep) val += la_to_f<T>(pep[(long)j * n + c0 + px]);
+                    if (pew) {   // + pe(v): depthwise 3x3 conv (+ bias) of v's plane j, evaluated at this pixel (v is L1 / L2 resident: it was just streamed)
+                        const int pidx = c0 + px, yy = pidx / pw, xx = pidx - yy * pw, ph = n / pw;
+                        const float* wj = pew + (long)(h * D + j) * 9;
+                        const T* vj = vp + (long)j * n;
+                        float acc9 = peb ? peb[h * D + j] : 0.f;
+#pragma unroll
+                        for (int dy = -1; dy <= 1; ++dy) {
+                            const int y2 = yy + dy;
+                            if (y2 < 0 || y2 >= ph) continue;
+#pragma unroll
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const int x2 = xx + dx;
+                                if (x2 >= 0 && x2 < pw) acc9 = fmaf(wj[(dy + 1) * 3 + dx + 1], la_to_f<T>(vj[(long)y2 * pw + x2]), acc9);
+                            }
+                        }
+                        val += acc9;
+                    }
                     op[(long)j * n + c0 + px] = la_from_f<T>(val);
                 }
             }
@@ -156,10 +174,10 @@ __global__ void __launch_bounds__(256, 3) recnext_linattn_kernel(const T* __rest
 }
 
 template <typename T>
-static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe, void* out,
-                               cudaStream_t s) {
+static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe,
+                               const float* pew, const float* peb, int pw, void* out, cudaStream_t s) {
     const int grid = B * heads;
-#define LA_CASE(DD) case DD: recnext_linattn_kernel<T, DD><<<grid, 256, 0, s>>>((const T*)q, (const T*)k, qb, kb, (const T*)v, (const T*)pe, (T*)out, heads, n); break;
+#define LA_CASE(DD) case DD: recnext_linattn_kernel<T, DD><<<grid, 256, 0, s>>>((const T*)q, (const T*)k, qb, kb, (const T*)v, (const T*)pe, pew, peb, pw, (T*)out, heads, n); break;
     switch (d) {
         LA_CASE(4) LA_CASE(8) LA_CASE(16) LA_CASE(20) LA_CASE(24) LA_CASE(28) LA_CASE(32) LA_CASE(40)
         default: return cudaErrorInvalidValue;
@@ -170,14 +188,16 @@ static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* q, co
 
 // 0 ok, 1 unsupported head_dim / dtype, 2 CUDA error in *err
 // q, k: [B, dim, n] each (k == q + dim * n elements: one [B, 2 dim, n] tensor); qb / kb: fp32 [dim] biases added before the elu, or null
+// pew / peb (nullable): fp32 depthwise 3x3 filters [dim, 9] and biases [dim] of the `pe` ConvNorm, applied to v inside the kernel (planes pw columns wide)
 int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe,
-                   void* out, cudaStream_t stream, cudaError_t* err) {
+                   const float* pew, const float* peb, int pw, void* out, cudaStream_t stream, cudaError_t* err) {
     if (heads < 1 || dim % heads != 0 || dtype < 0 || dtype > 2) return 1;
+    if (pew && (pw < 1 || n % pw != 0)) return 1;
     const int d = dim / heads;
     if (!(d == 4 || d == 8 || d == 16 || d == 20 || d == 24 || d == 28 || d == 32 || d == 40)) return 1;
-    *err = dtype == 0 ? la_launch_t<float>(B, heads, d, n, q, k, qb, kb, v, pe, out, stream)
-         : dtype == 1 ? la_launch_t<__nv_bfloat16>(B, heads, d, n, q, k, qb, kb, v, pe, out, stream)
-                      : la_launch_t<__half>(B, heads, d, n, q, k, qb, kb, v, pe, out, stream);
+    *err = dtype == 0 ? la_launch_t<float>(B, heads, d, n, q, k, qb, kb, v, pe, pew, peb, pw, out, stream)
+         : dtype == 1 ? la_launch_t<__nv_bfloat16>(B, heads, d, n, q, k, qb, kb, v, pe, pew, peb, pw, out, stream)
+                      : la_launch_t<__half>(B, heads, d, n, q, k, qb, kb, v, pe, pew, peb, pw, out, stream);
     return *err == cudaSuccess ? 0 : 2;
 }
 

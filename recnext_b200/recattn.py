@@ -186,6 +186,31 @@ def linattn_forward_qk(q: torch.Tensor, k: torch.Tensor, qbias: Optional[torch.T
     return out
 
 
+def linattn_forward_pe(q: torch.Tensor, k: torch.Tensor, qbias, kbias, v: torch.Tensor, pe_w: torch.Tensor, pe_b: Optional[torch.Tensor],
+                       num_heads: int) -> torch.Tensor:
+    """``linattn_forward_qk`` with the depthwise 3x3 ``pe`` ConvNorm (BatchNorm folded: pe_w [dim, 1, 3, 3], pe_b [dim]) evaluated on v inside the
+    kernel (``recnext_linattn_forward_pe``): everything of LinearAttention1/2.forward after the ``qk`` GEMMs is one launch."""
+    if not v.is_cuda:
+        raise RuntimeError("recnext_b200.linattn_forward_pe runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if v.dtype not in _DTYPES:
+        raise TypeError(f"linattn_forward_pe: float32 / bfloat16 / float16 only, got {v.dtype}")
+    v = v.contiguous()
+    q, k = q.to(v.dtype).contiguous(), k.to(v.dtype).contiguous()
+    B, dim, H, W = v.shape
+    if q.numel() != v.numel() or k.numel() != v.numel() or pe_w.numel() != dim * 9:
+        raise ValueError(f"linattn_forward_pe: q {tuple(q.shape)} / k {tuple(k.shape)} / pe_w {tuple(pe_w.shape)} do not match v {tuple(v.shape)}")
+    f32 = lambda t: None if t is None else t.detach().float().contiguous()  # noqa: E731
+    qb, kb, pw, pb = f32(qbias), f32(kbias), f32(pe_w), f32(pe_b)
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        ev = _timing_start()
+        N.check(N.lib().recnext_linattn_forward_pe(B, dim, num_heads, H, W, _DTYPES[v.dtype], q.data_ptr(), k.data_ptr(), ptr(qb), ptr(kb), v.data_ptr(),
+                                                   ptr(pw), ptr(pb), out.data_ptr(), _stream(v)), "recnext_linattn_forward_pe")
+        _timing_stop(ev, 4 * v.numel() * v.element_size(), ("linattn",) + tuple(v.shape))
+    return out
+
+
 def _no_grad_wanted(x, module, what):
     """The A-series kernels have no backward: refuse to cut a gradient silently (an eval-mode model stays differentiable in the reference)."""
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
@@ -205,7 +230,8 @@ class _LinearAttention(nn.Module):
     q, k = elu(qk(x)) + 1;  out = q^T (k v^T / n) / (q^T mean(k) + 1e-6) + pe(x).  Sub-module names (``qk``, ``pe``) and therefore the
     ``state_dict`` are the reference's.  The grouped (groups = 2) 1x1 ``qk`` ConvNorm is two plain GEMMs per image, W_q x[: dim/2] and
     W_k x[dim/2 :]: the library's grouped-conv kernels for it are SGEMM-class (15 % of an A3 step with their bias adds), so it runs as two
-    batched tensor-core GEMMs (``torch.bmm`` on the BatchNorm-folded weights, cuBLAS) whose bias the attention kernel adds before the elu.
+    batched tensor-core GEMMs (``torch.bmm`` on the BatchNorm-folded weights, cuBLAS) whose bias the attention kernel adds before the elu; the
+    depthwise 3x3 ``pe`` ConvNorm is evaluated on v inside the attention kernel (``recnext_linattn_forward_pe``).
     Inference only: there is no backward and, deliberately, no PyTorch fallback — anything the kernel does not serve raises."""
 
     def __init__(self, dim, num_heads, conv_bias=False):
@@ -215,6 +241,19 @@ class _LinearAttention(nn.Module):
         self.qk = ConvNorm(dim, dim * 2, kernel_size=1, groups=2, bias=conv_bias)   # (conv_bias: the L-series ConvNorm keeps the conv's bias,
         self.pe = ConvNorm(dim, dim, kernel_size=3, padding=1, groups=dim, bias=conv_bias)   #  lsnet/model/recattn.py:128-146)
         self._qk_cache = None
+        self._pe_cache = None
+
+    def _pe_params(self, device):
+        """BatchNorm-folded `pe` filters [dim, 9] and bias [dim] (fp32); cached like the `qk` weights."""
+        m = self.pe
+        src = [m.conv.weight, m.conv.bias, m.norm.weight, m.norm.bias, m.norm.running_mean, m.norm.running_var] if isinstance(m, ConvNorm) else [m.weight, m.bias]
+        key = (device,) + tuple((id(t), t._version) for t in src if t is not None)
+        c = self._pe_cache
+        if c is None or c[0] != key:
+            w, b = _wb(m)
+            c = (key, w.detach().float().reshape(w.shape[0], 9).contiguous(), None if b is None else b.detach().float().contiguous())
+            self._pe_cache = c
+        return c[1], c[2]
 
     def _qk_params(self, dtype, device):
         """BatchNorm-folded `qk` weights as [2, dim, dim / 2] in the activation dtype and the fp32 bias [2 dim]; cached, keyed on the version
@@ -248,6 +287,10 @@ class _LinearAttention(nn.Module):
         xg = x.view(B, 2, dim // 2, H * W)
         q = torch.bmm(w[0].expand(B, dim, dim // 2), xg[:, 0])     # [B, dim, n]: batched GEMMs with the weight broadcast over the batch (stride 0)
         k = torch.bmm(w[1].expand(B, dim, dim // 2), xg[:, 1])
+        pe_conv = self.pe.conv if isinstance(self.pe, ConvNorm) else self.pe
+        if tuple(pe_conv.kernel_size) == (3, 3) and tuple(pe_conv.padding) == (1, 1) and tuple(pe_conv.stride) == (1, 1) and pe_conv.groups == dim:
+            pw, pb = self._pe_params(x.device)
+            return linattn_forward_pe(q, k, b[:dim], b[dim:], x, pw, pb, self.num_heads)    # `pe` evaluated inside the kernel
         return linattn_forward_qk(q, k, b[:dim], b[dim:], x, self.pe(x), self.num_heads)
 
 
