@@ -390,6 +390,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra objects (train_ddp, a_series, detection, gpu_eager_baseline)")
+    ap.add_argument("--no-graph", action="store_true", help="e2e leg: launch the kernels eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--model", default=MODEL, help="recnext_m0..m5 / recnext_a0..a5 (default: the metric's recnext_m3)")
     ap.add_argument("--train", action="store_true",
                     help="BASELINE.json configs[2]: training step (fwd + bwd + AdamW, bf16 autocast, DDP over NCCL when launched with torchrun) "
@@ -479,7 +480,7 @@ def main():
     # host memory and its logits back; the copy of batch i+1 overlaps the compute of batch i (separate copy stream)
     from recnext_b200.infer import PipelinedInference
 
-    runner = PipelinedInference(net, torch.bfloat16, dev)
+    runner = PipelinedInference(net, torch.bfloat16, dev, cuda_graph=not args.no_graph)
 
     def run_e2e(steps):
         n = 0
@@ -589,7 +590,7 @@ def main():
                    "l2": "per-step activations (>= 100 MB per stage-0 tensor) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": x_host.numel() * 2,
-                "d2h_bytes_per_step": y_host.numel() * 2, "api": "recnext_b200.infer.PipelinedInference(model).run(pinned host batches) -> pinned host logits (H2D of batch i+1 overlaps compute of batch i)"},
+                "d2h_bytes_per_step": y_host.numel() * 2, "api": "recnext_b200.infer.PipelinedInference(model%s).run(pinned host batches) -> pinned host logits (H2D of batch i+1 overlaps compute of batch i)" % ("" if args.no_graph else ", cuda_graph=True")},
         "gpu_launches": n_launch,
         "roofline": roofline,
     }

@@ -19,13 +19,43 @@ class PipelinedInference:
     host buffers used in rotation, so a yielded tensor stays valid until the next-but-one ``next()`` (while result i is in
     the consumer's hands, result i+1 is being copied out and result i+2 goes to the third buffer)."""
 
-    def __init__(self, model: torch.nn.Module, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, device: Optional[torch.device] = None):
+    def __init__(self, model: torch.nn.Module, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, device: Optional[torch.device] = None,
+                 cuda_graph: bool = False):
+        """``cuda_graph=True``: the forward of each of the two staging buffers is captured once in a CUDA graph (after an eager warm-up run
+        that fills the packed-weight caches) and replayed afterwards — one graph launch per batch instead of ~50 kernel launches plus the
+        Python between them.  Every kernel of the eval path is stream-ordered and allocation-free, so the capture is legal
+        (tests/test_model.py::test_whole_model_is_cuda_graph_capturable); the graphs are rebuilt when the batch shape changes."""
         self.model = model.eval()
         self.dtype = autocast_dtype
         self.device = device or next(model.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.device)
         self._xin = [None, None]
         self._yout = [None, None, None]
+        self.cuda_graph = cuda_graph
+        self._graphs = [None, None]      # (graph, static output) per staging buffer
+
+    def _forward(self, cur: int) -> torch.Tensor:
+        x = self._xin[cur]
+        if not self.cuda_graph:
+            with torch.autocast("cuda", dtype=self.dtype, enabled=self.dtype is not None):
+                return self.model(x)
+        g = self._graphs[cur]
+        if g is None or g[2] is not x:
+            with torch.autocast("cuda", dtype=self.dtype, enabled=self.dtype is not None):
+                self.model(x)                                     # eager warm-up on this very buffer (weight caches, kernel attributes)
+            main = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(main)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    with torch.autocast("cuda", dtype=self.dtype, enabled=self.dtype is not None):
+                        y = self.model(x)
+            main.wait_stream(side)
+            g = (graph, y, x)
+            self._graphs[cur] = g
+        g[0].replay()
+        return g[1]
 
     def _stage(self, i: int, xh: torch.Tensor) -> torch.cuda.Event:
         """copy host batch -> device staging buffer i on the copy stream; returns the event that marks its arrival"""
@@ -55,8 +85,7 @@ class PipelinedInference:
         while nxt is not None:
             cur = i & 1
             main.wait_event(arrived)
-            with torch.autocast("cuda", dtype=self.dtype, enabled=self.dtype is not None):
-                y = self.model(self._xin[cur])
+            y = self._forward(cur)
             consumed[cur] = torch.cuda.Event()
             consumed[cur].record(main)
             try:
