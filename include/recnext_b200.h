@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RECNEXT_ABI_VERSION 2
+#define RECNEXT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RECNEXT_API __attribute__((visibility("default")))

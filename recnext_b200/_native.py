@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_lib", "librecnext_b200.so")
 MAX_LEVEL = 6
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16, F16 = 0, 1, 2
 BILINEAR, NEAREST = 0, 1
