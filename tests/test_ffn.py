@@ -167,3 +167,20 @@ def test_downsample_block_fused_matches_library_path(monkeypatch):
     assert y.dtype == torch.bfloat16 and tuple(y.shape) == (4, 128, 28, 28)
     assert rel_err(y.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
     assert rel_err(y_lib.float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16
+
+
+@pytest.mark.gpu
+def test_dwdown_full_size_batch_slices_bit_identical():
+    """BASELINE configs[1] stage borders at batch 256: plane groups never mix (an image computed inside the batch equals the image alone)"""
+    from recnext_b200.model import dwdown_forward
+
+    for C, H in ((64, 56), (128, 28), (256, 14)):
+        torch.manual_seed(C)
+        x = torch.randn(256, C, H, H, device="cuda").bfloat16()
+        w = torch.randn(2 * C, 1, 7, 7, device="cuda") / 7.0
+        b = 0.1 * torch.randn(2 * C, device="cuda")
+        full = dwdown_forward(x, w, b)
+        for i in (0, 77, 255):
+            assert torch.equal(dwdown_forward(x[i:i + 1].contiguous(), w, b)[0], full[i])
+        ref = F.conv2d(x[:2].float(), w, b, stride=2, padding=3, groups=C)
+        assert rel_err(full[:2].float().cpu().numpy(), ref.cpu().numpy()) < TOL_BF16

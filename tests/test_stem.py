@@ -108,3 +108,23 @@ def test_stem_module_switch():
     assert m._stem_cache is None
     with torch.autocast("cuda", dtype=torch.bfloat16):
         assert not m._fused_ok(x)                   # training mode / gradients wanted: the differentiable graph runs
+
+
+@pytest.mark.gpu
+def test_full_size_batch_slices_bit_identical():
+    """BASELINE configs[1] size (256 x 3 x 224 x 224): every image is computed exactly as it is alone (tiles never mix images; no atomics), and
+    the interior agrees with the library graph on a sample of images"""
+    from recnext_b200.model import stem_forward, stem_pack
+
+    m, replace_batchnorm = _stem(64)
+    replace_batchnorm(m)
+    m = m.cuda()
+    pk = stem_pack(m.stem[0], m.stem[2], torch.bfloat16)
+    x = torch.randn(256, 3, 224, 224, device="cuda").bfloat16()
+    with torch.no_grad():
+        full = stem_forward(x, *pk)
+        for b in (0, 101, 255):
+            assert torch.equal(stem_forward(x[b:b + 1].contiguous(), *pk)[0], full[b])
+        ref = _reference(x[:4].float(), m.stem[0], m.stem[2], torch.bfloat16)
+    assert tuple(full.shape) == (256, 64, 56, 56)
+    assert rel_err(full[:4].float().cpu().numpy(), ref.cpu().numpy()) < 8e-3
