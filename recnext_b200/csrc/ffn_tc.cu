@@ -11,12 +11,18 @@
 //     GEMM2  D2[C x NT]   += W2[:, hc] (C x 128)   . H[hc] (128 x NT)    accumulators in TMEM for the whole tile
 // and finally EPI2 out = D2 + b2 + x.  The hidden activation never leaves the SM; HBM traffic is 3 N e.
 //
-// Warp roles (448 threads, one CTA per SM):
-//   warps 0-7   epilogue: TMEM -> registers (tcgen05.ld) -> bias / GELU / residual -> shared memory or global memory
+// Warp roles (512 threads, one CTA per SM):
+//   warps 0-7   epilogue, two ping-pong groups of four: TMEM -> registers (tcgen05.ld) -> bias / GELU -> H in shared memory; at the end of a
+//               tile D2 + b2 -> 16-bit rows in the group's (then free) H buffer, one 128-channel tile at a time: the accumulator leaves
+//               TMEM without waiting for global memory
 //   warp  8     weight producer: one elected lane streams the PRE-PACKED weight tiles (16 KB, exactly the shared-memory image
-//               of a 128 x 64 K-major operand) through a 4-slot ring with TMA bulk copies (cp.async.bulk + mbarrier tx counts)
+//               of a 128 x 64 K-major operand) through a 4..8-slot ring with TMA bulk copies (cp.async.bulk + mbarrier tx counts)
 //   warp  9     MMA issuer: one elected lane issues every tcgen05.mma; tcgen05.commit releases ring slots / publishes accumulators
-//   warps 10-13 activation loaders: Y tile global -> shared memory in the MN-major core-matrix layout (16-byte chunks)
+//   warps 10-11 activation loaders: Y tile global -> shared memory in the MN-major core-matrix layout (cp.async, 16-byte chunks); with one
+//               tile buffer (C >= 256) the tile is handed over in 64-channel slabs, each with its own barriers
+//   warps 12-15 output writers: staged rows + residual x -> out, lanes along the pixels (coalesced), row cursors, residual prefetched
+// Planes whose size is not a multiple of 4 pixels (7 x 7) are padded to a multiple of 8 columns in TILE space (FfnTcPlan::HWp): no 8-pixel
+// chunk straddles two images and the padding columns are never stored.
 // All hand-offs are mbarriers; the MMA stream is software pipelined (GEMM1 of chunk s + 1 is issued before GEMM2 of chunk s) so the
 // tensor pipe works while the epilogue warps run the GELU of chunk s.
 #include <cuda_runtime.h>
