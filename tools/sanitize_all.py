@@ -39,5 +39,16 @@ for (d, heads, n) in [(32, 2, 784), (20, 2, 100), (40, 2, 49), (8, 2, 16)]:
     for dt in (torch.float32, torch.bfloat16):
         o = linattn_forward(torch.randn(2, 2 * d * heads, 1, n, device=dev).to(dt), torch.randn(2, d * heads, 1, n, device=dev).to(dt), None, heads)
     print("linattn", (d, heads, n), float(o.float().abs().mean()))
+from recnext_b200.recattn import linattn_forward_pe, linattn_forward_qk
+for (d, heads, h, w) in [(32, 2, 28, 28), (20, 2, 7, 9), (8, 2, 4, 4)]:
+    dim = d * heads
+    for dt in (torch.float32, torch.bfloat16):
+        q = torch.randn(2, dim, h, w, device=dev).to(dt); k = torch.randn_like(q); v = torch.randn_like(q)
+        o = linattn_forward_qk(q, k, torch.randn(dim, device=dev), torch.randn(dim, device=dev), v, torch.randn_like(v), heads)
+        o = linattn_forward_pe(q, k, torch.randn(dim, device=dev), None, v, torch.randn(dim, 1, 3, 3, device=dev), torch.randn(dim, device=dev), heads)
+    print("linattn qk/pe", (d, heads, h, w), float(o.float().abs().mean()))
+xa = torch.randn(2, 8, 25, 21, device=dev); wa = torch.randn(8, 1, 5, 5, device=dev) * 0.1; ba = torch.randn(8, device=dev) * 0.1
+lowa = R.recattn_down_forward(xa, wa, ba); ya = R.recattn_up_forward(xa, lowa, wa, ba, "bilinear")      # fp32 RecAttn pieces (gstream.cu)
+print("recattn fp32", float(ya.abs().mean()))
 torch.cuda.synchronize()
 print("done")
