@@ -169,7 +169,7 @@ RECNEXT_API int recnext_stem_forward(int32_t B, int32_t H, int32_t W, int32_t C1
  *     self.norm(self.token_mixer(x))      model/recnext.py:137-138,145
  * x: [B, C, H, W], out: [B, 2C, (H-1)/2+1, (W-1)/2+1] in dtype (RECNEXT_F32 | RECNEXT_BF16 | RECNEXT_F16; fp32 arithmetic);
  * w: [2C, 1, 7, 7] fp32, b: [2C] fp32.
- * Inference entry point.  RECNEXT_EUNSUPPORTED if a padded fp32 plane does not fit in shared memory.
+ * out must be 16-byte aligned.  Inference entry point.  RECNEXT_EUNSUPPORTED if a padded plane does not fit in shared memory.
  */
 RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t W, int32_t dtype, const void* x, const float* w,
                                        const float* b, void* out, void* stream);

@@ -403,6 +403,7 @@ RECNEXT_API int recnext_dwdown_forward(int32_t B, int32_t C, int32_t H, int32_t 
     if (B < 0 || C < 1 || H < 1 || W < 1) return fail(RECNEXT_EINVAL, "recnext_dwdown_forward: bad shape [%d,%d,%d,%d]", B, C, H, W);
     if (B == 0) return RECNEXT_OK;
     if (!x || !w || !b || !out) return fail(RECNEXT_EINVAL, "recnext_dwdown_forward: null tensor");
+    if ((((uintptr_t)out) & 15) != 0 || (((uintptr_t)x) & 1) != 0) return fail(RECNEXT_EINVAL, "recnext_dwdown_forward: out must be 16-byte aligned (vector stores)");
     cudaError_t e = cudaSuccess;
     const int rc = dwdown_launch(B, C, H, W, dtype, x, w, b, out, (cudaStream_t)stream, &e);
     if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "recnext_dwdown_forward: a padded fp32 %dx%d plane must fit in shared memory", H, W);
