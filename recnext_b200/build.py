@@ -21,7 +21,7 @@ LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "librecnext_b200.so")
 OBJDIR = os.path.join(ROOT, "build", "obj")
 
-SOURCES = ["capi.cu", "recconv_k3.cu", "recconv_k5.cu", "recconv_k7.cu", "recconv_w3.cu", "recconv_w5.cu", "recconv_w7.cu", "recconv_m5.cu", "recconv_mb5.cu", "ffn_mma.cu", "dwdown.cu", "linattn.cu", "gstream.cu", "ffn_tc.cu", "stem.cu"]
+SOURCES = ["capi.cu", "recconv_k3.cu", "recconv_k5.cu", "recconv_k7.cu", "recconv_w3.cu", "recconv_w5.cu", "recconv_w7.cu", "recconv_m5.cu", "recconv_mb5.cu", "ffn_mma.cu", "dwdown.cu", "linattn.cu", "linattn_mma.cu", "gstream.cu", "ffn_tc.cu", "stem.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

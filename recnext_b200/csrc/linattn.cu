@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace recnext {
 
@@ -187,6 +188,10 @@ static cudaError_t la_launch_t(int B, int heads, int d, int n, const void* q, co
 }
 
 // 0 ok, 1 unsupported head_dim / dtype, 2 CUDA error in *err
+// tensor-core version for 16-bit activations (linattn_mma.cu)
+cudaError_t linattn_mma_launch(int B, int heads, int d, int n, int dtype, const void* q, const void* k, const float* qb, const float* kb, const void* v,
+                               const void* pe, const float* pew, const float* peb, int pw, void* out, cudaStream_t stream);
+
 // q, k: [B, dim, n] each (k == q + dim * n elements: one [B, 2 dim, n] tensor); qb / kb: fp32 [dim] biases added before the elu, or null
 // pew / peb (nullable): fp32 depthwise 3x3 filters [dim, 9] and biases [dim] of the `pe` ConvNorm, applied to v inside the kernel (planes pw columns wide)
 int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* q, const void* k, const float* qb, const float* kb, const void* v, const void* pe,
@@ -195,6 +200,13 @@ int linattn_launch(int B, int dim, int heads, int n, int dtype, const void* q, c
     if (pew && (pw < 1 || n % pw != 0)) return 1;
     const int d = dim / heads;
     if (!(d == 4 || d == 8 || d == 16 || d == 20 || d == 24 || d == 28 || d == 32 || d == 40)) return 1;
+    // 16-bit activations: the contractions run on the tensor cores (RECNEXT_LINATTN=fma keeps the FP32-FMA kernel: A/B measurements)
+    static int use_fma = -1;
+    if (use_fma < 0) { const char* e = getenv("RECNEXT_LINATTN"); use_fma = (e && e[0] == 'f') ? 1 : 0; }
+    if (dtype != 0 && !use_fma && (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0) {
+        *err = linattn_mma_launch(B, heads, d, n, dtype, q, k, qb, kb, v, pe, pew, peb, pw, out, stream);
+        return *err == cudaSuccess ? 0 : 2;
+    }
     *err = dtype == 0 ? la_launch_t<float>(B, heads, d, n, q, k, qb, kb, v, pe, pew, peb, pw, out, stream)
          : dtype == 1 ? la_launch_t<__nv_bfloat16>(B, heads, d, n, q, k, qb, kb, v, pe, pew, peb, pw, out, stream)
                       : la_launch_t<__half>(B, heads, d, n, q, k, qb, kb, v, pe, pew, peb, pw, out, stream);

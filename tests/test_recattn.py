@@ -205,6 +205,37 @@ def test_cuda_linear_attention_head_dims(d, heads, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=["bf16", "f16", "f32"])
+@pytest.mark.parametrize("d,heads,h,w", [(32, 2, 28, 28), (32, 4, 14, 14), (32, 8, 7, 7), (32, 16, 4, 4), (20, 2, 9, 13), (40, 2, 10, 13), (24, 3, 5, 5),
+                                         (28, 2, 12, 12), (8, 2, 1, 1), (16, 2, 3, 40), (4, 3, 17, 8)])
+def test_cuda_linear_attention_qk_bias_pe_entries(d, heads, h, w, dtype):
+    """recnext_linattn_forward_qk / _pe (separate q / k tensors, biases added before the elu, the depthwise 3x3 `pe` conv evaluated inside
+    the kernel) against the same formula in fp32 PyTorch: tensor-core kernel for 16-bit activations (every plane size class: 8-, 4- and
+    1-pixel global accesses, several chunks, partial chunks, single pixels), FP32-FMA kernel for fp32"""
+    from recnext_b200.recattn import linattn_forward_pe, linattn_forward_qk
+
+    torch.manual_seed(d + h)
+    B, dim, n = 3, d * heads, h * w
+    q = torch.randn(B, dim, h, w, device="cuda").to(dtype); k = torch.randn_like(q); v = torch.randn_like(q)
+    qb, kb = 0.3 * torch.randn(dim, device="cuda"), 0.3 * torch.randn(dim, device="cuda")
+    pw, pb = 0.3 * torch.randn(dim, 1, 3, 3, device="cuda"), 0.1 * torch.randn(dim, device="cuda")
+    pe = F.conv2d(v.float(), pw, pb, padding=1, groups=dim)
+    r16 = (lambda t: t.to(dtype).float())          # the kernels hold q, k (after the elu) and kv in the activation dtype, as the autocast graph does
+    qq = r16(F.elu(q.float() + qb.view(1, -1, 1, 1)) + 1.0).view(B, heads, d, n)
+    kk = r16(F.elu(k.float() + kb.view(1, -1, 1, 1)) + 1.0).view(B, heads, d, n)
+    vv = v.float().view(B, heads, d, n)
+    kvm = (kk @ vv.transpose(-1, -2)) / n
+    num = qq.transpose(-1, -2) @ kvm
+    den = qq.transpose(-1, -2) @ kk.mean(dim=-1, keepdim=True) + 1e-6
+    ref = (num / den).transpose(-1, -2).reshape(B, dim, h, w) + pe
+    tol = {torch.bfloat16: 1.5e-2, torch.float16: 3e-3, torch.float32: 2e-5}[dtype]
+    out_pe = linattn_forward_pe(q, k, qb, kb, v, pw, pb, heads)
+    assert rel_err(out_pe.float().cpu().numpy(), ref.cpu().numpy()) < tol
+    out_qk = linattn_forward_qk(q, k, qb, kb, v, pe.to(dtype), heads)
+    assert rel_err(out_qk.float().cpu().numpy(), ref.cpu().numpy()) < tol
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("path", FIX, ids=lambda p: os.path.basename(p)[8:-4])
 def test_cuda_linear_attention_fp32_parity(path):
     """fp32 bar of the north star (1e-5) for the linear-attention kernel: fixture inputs/outputs of the unmodified reference"""

@@ -40,7 +40,7 @@ for (d, heads, n) in [(32, 2, 784), (20, 2, 100), (40, 2, 49), (8, 2, 16)]:
         o = linattn_forward(torch.randn(2, 2 * d * heads, 1, n, device=dev).to(dt), torch.randn(2, d * heads, 1, n, device=dev).to(dt), None, heads)
     print("linattn", (d, heads, n), float(o.float().abs().mean()))
 from recnext_b200.recattn import linattn_forward_pe, linattn_forward_qk
-for (d, heads, h, w) in [(32, 2, 28, 28), (20, 2, 7, 9), (8, 2, 4, 4)]:
+for (d, heads, h, w) in [(32, 2, 28, 28), (20, 2, 7, 9), (8, 2, 4, 4), (40, 2, 10, 13), (32, 2, 14, 14)]:
     dim = d * heads
     for dt in (torch.float32, torch.bfloat16):
         q = torch.randn(2, dim, h, w, device=dev).to(dt); k = torch.randn_like(q); v = torch.randn_like(q)
