@@ -343,6 +343,14 @@ static int recattn_launch(const recconv_desc* d, int variant, const void* w, con
     opt.num_sms = device_sms();
     opt.variant = variant; opt.zH = zH; opt.zW = zW;
     if (const char* e = getenv("RECNEXT_MDBG")) opt.dbg = atoi(e);
+    if (const char* e = getenv("RECNEXT_AG")) opt.force_G = atoi(e);       // team-shape experiments (tools/ra_prof.py)
+    if (const char* e = getenv("RECNEXT_ATW")) opt.force_TW = atoi(e);
+    if (const char* e = getenv("RECNEXT_ANT")) opt.force_NT = atoi(e);
+    if (getenv("RECNEXT_APLAN")) {
+        MPlan q;
+        if (m_make_plan(q, d->B, d->C, d->H, d->W, d->k, 1, d->mode, d->dtype, d->wdtype, d->has_bias, opt) == 0)
+            fprintf(stderr, "[recattn variant %d %dx%d] G=%d TW=%d NTEAM=%d threads=%d smem=%d grid=%d tma=%d\n", variant, d->H, d->W, q.G, q.TW, q.NTEAM, q.threads, q.smem_bytes, q.grid, q.use_tma);
+    }
     MPlan mp;
     const int rc = m_make_plan(mp, d->B, d->C, d->H, d->W, d->k, 1, d->mode, d->dtype, d->wdtype, d->has_bias, opt);
     if (rc == 1) return fail(RECNEXT_EUNSUPPORTED, "%s: a %dx%d plane does not fit in 227 KB of shared memory", what, d->H, d->W);

@@ -561,7 +561,7 @@ __device__ __forceinline__ void m_up2x_mma(const MTeam<T>& tm, int l) {
 // count is a compile-time constant and every loop over levels is fully unrolled, so that with a constexpr `pl`
 // all sizes, pitches and offsets become immediates.
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int LS>
+template <typename T, int LS, int VS = -1>
 __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, const KernelArgs& a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -569,7 +569,7 @@ __device__ __forceinline__ void m_fwd_body(const MPlan& pl, const MPlan& rt, con
     const uint32_t smem32 = rc_smem_u32(smem);
     MTeam<T> tm{pl, rt, smem32, smem32 + (uint32_t)(pl.smTeams + team * pl.team_bytes), team, wt, lane, wt * 32 + lane};
     const int L = LS >= 0 ? LS : pl.L, G = pl.G;
-    const int variant = LS >= 0 ? 0 : rt.variant;   // the specialised kernels serve RecConv2d only
+    const int variant = VS >= 0 ? VS : (LS >= 0 ? 0 : rt.variant);   // compile-time in the specialised kernels (RecConv2d: 0; RecAttn2d pieces: 1 / 2)
     const int lg = lane >> 2, lt = lane & 3;
 
     // ---- CTA init: zero the team slices (the borders of the padded buffers stay zero), interpolation tables, mbarriers
@@ -786,25 +786,26 @@ template <typename T>
 __global__ void __launch_bounds__(512, 1) recconv_mfwd_kernel(const __grid_constant__ MPlan pl, const __grid_constant__ KernelArgs a) {
     m_fwd_body<T, -1>(pl, pl, a);
 }
-// specialised kernel: plane geometry (H0 x W0, L0 levels, G0 planes per batch) fixed at compile time
-template <typename T, int H0, int W0, int L0, int G0>
+// specialised kernel: plane geometry (H0 x W0, L0 levels, G0 planes per batch), variant (0 RecConv2d, 1 / 2 the RecAttn2d pieces) and
+// interpolation mode fixed at compile time
+template <typename T, int H0, int W0, int L0, int G0, int V0 = 0, int MODE0 = 0>
 __global__ void __launch_bounds__(32 * m_static_max_warps(H0, W0), 1) recconv_mfwd_static_kernel(const __grid_constant__ MPlan rt, const __grid_constant__ KernelArgs a) {
-    constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1);
-    m_fwd_body<T, L0>(sp, rt, a);
+    constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1, V0, MODE0);
+    m_fwd_body<T, L0, V0>(sp, rt, a);
 }
 
-template <typename T, int H0, int W0, int L0, int G0>
+template <typename T, int H0, int W0, int L0, int G0, int V0 = 0, int MODE0 = 0>
 inline bool m_try_static(const MPlan& pl, const KernelArgs& a, cudaStream_t stream, cudaError_t& err) {
-    constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1);
-    if (pl.variant != 0 || pl.H != H0 || pl.W != W0 || pl.L != L0 || pl.G != G0) return false;
+    constexpr MPlan sp = m_static_plan(H0, W0, L0, G0, std::is_same<T, __half>::value ? 2 : 1, V0, MODE0);
+    if (pl.variant != V0 || pl.mode != MODE0 || pl.H != H0 || pl.W != W0 || pl.L != L0 || pl.G != G0) return false;
     const MPlan st = m_static_patched(sp, pl);
     if (memcmp(&st, &pl, sizeof(MPlan)) != 0) return false;
     static DeviceOnce configured = {};
     err = rc_once_per_device(configured, [] {
-        return cudaFuncSetAttribute(recconv_mfwd_static_kernel<T, H0, W0, L0, G0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        return cudaFuncSetAttribute(recconv_mfwd_static_kernel<T, H0, W0, L0, G0, V0, MODE0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (err != cudaSuccess) return true;
-    recconv_mfwd_static_kernel<T, H0, W0, L0, G0><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
+    recconv_mfwd_static_kernel<T, H0, W0, L0, G0, V0, MODE0><<<pl.grid, pl.threads, pl.smem_bytes, stream>>>(pl, a);
     err = cudaGetLastError();
     return true;
 }
@@ -831,6 +832,18 @@ inline cudaError_t m_launch_fwd_t(const MPlan& pl, const KernelArgs& a, cudaStre
         if (m_try_static<T, 28, 28, 3, 1>(pl, a, stream, err)) return err;
         if (m_try_static<T, 14, 14, 2, 4>(pl, a, stream, err)) return err;
         if (m_try_static<T, 7, 7, 1, 8>(pl, a, stream, err)) return err;
+        // the RecAttn2d pieces of the A-series at the same stage shapes (model/recattn.py:54-67: one level, mode 'nearest')
+        if (pl.variant == 1) {
+            if (m_try_static<T, 56, 56, 1, 1, 1, 1>(pl, a, stream, err)) return err;
+            if (m_try_static<T, 28, 28, 1, 1, 1, 1>(pl, a, stream, err)) return err;
+            if (m_try_static<T, 14, 14, 1, 4, 1, 1>(pl, a, stream, err)) return err;
+            if (m_try_static<T, 7, 7, 1, 8, 1, 1>(pl, a, stream, err)) return err;
+        } else if (pl.variant == 2) {
+            if (m_try_static<T, 56, 56, 1, 1, 2, 1>(pl, a, stream, err)) return err;
+            if (m_try_static<T, 28, 28, 1, 1, 2, 1>(pl, a, stream, err)) return err;
+            if (m_try_static<T, 14, 14, 1, 4, 2, 1>(pl, a, stream, err)) return err;
+            if (m_try_static<T, 7, 7, 1, 8, 2, 1>(pl, a, stream, err)) return err;
+        }
     }
     static DeviceOnce configured = {};
     err = rc_once_per_device(configured, [] { return cudaFuncSetAttribute(recconv_mfwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });

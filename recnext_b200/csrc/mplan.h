@@ -221,12 +221,14 @@ RC_HD constexpr int m_static_max_warps(int H, int W) { return (H <= 0 && W <= 0)
 // (mfwd.cuh): every level size, pitch and offset folds into immediates.  The host compares it field by field with
 // the run-time plan before choosing a specialised kernel; B, C, grid, bias, parameter dtype and TMA eligibility
 // stay run-time values.
-RC_HD constexpr MPlan m_static_plan(int H, int W, int L, int G, int dtype) {
+RC_HD constexpr MPlan m_static_plan(int H, int W, int L, int G, int dtype, int variant = 0, int mode = 0) {
     MPlan pl{};
     MPlanOptions o{};
     o.force_G = G;
     o.max_warps = m_static_max_warps(H, W);
-    m_make_plan(pl, 1, G, H, W, 5, L, 0, dtype, dtype, 0, o);
+    o.variant = variant;
+    if (variant == 2) { o.zH = rc_down_size(H, 5); o.zW = rc_down_size(W, 5); }   // RecAttn2d: z has the size of down(x)
+    m_make_plan(pl, 1, G, H, W, 5, L, mode, dtype, dtype, 0, o);
     return pl;
 }
 // copies the run-time fields of `rt` into a static plan so that the two can be compared with memcmp
