@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) recnext_linattn_mma_kernel(const T* __res
     // a chunk row (one channel, 128 pixels) -> shared memory, transformed; pixels past n are zero (also in the ones row: handled by `cn` below)
     // Only the first `cw` pixels of a row are touched (cw = cn rounded up to a power of two >= 16: the MMAs read whole 16-pixel steps, and
     // shifts replace divisions): small planes (7 x 7, 4 x 4) do not pay for 128-pixel rows.
+    const bool flat = n <= kCH && ((D * n) & 7) == 0 && (n & 3) != 0 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(pe)) & 15) == 0;
     auto load_rows = [&](const unsigned short* src, unsigned short* dst, const float* bias, bool act, int c0, int cn) {
         int cwl = 4;
         while ((1 << cwl) < cn) ++cwl;
@@ -111,6 +112,24 @@ __global__ void __launch_bounds__(256) recnext_linattn_mma_kernel(const T* __res
                 }
                 if (vw == 8) *reinterpret_cast<uint4*>(dst + row * RP + px) = make_uint4(w[0], w[1], w[2], w[3]);
                 else *reinterpret_cast<uint2*>(dst + row * RP + px) = make_uint2(w[0], w[1]);
+            }
+        } else if (flat) {
+            // odd plane sizes that fit one chunk (7 x 7): the [D x n] block of this (image, head) is CONTIGUOUS and 16-byte aligned, so it is
+            // read as flat 16-byte vectors and scattered into the rows (one division per vector instead of 2-byte loads with one each)
+            const int cw = 1 << cwl;
+            for (int i = tid; i < D * (cw - n); i += 256) { const int row = i / (cw - n); dst[row * RP + n + (i - row * (cw - n))] = 0; }
+            for (int i = tid; i < (D * n) / 8; i += 256) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                int row = (8 * i) / n, px = 8 * i - row * n;
+                float bb = (act && bias) ? bias[row] : 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    unsigned short val = (unsigned short)((w[e >> 1] >> (16 * (e & 1))) & 0xffffu);
+                    if (act) val = LH<T>::from_f(la_elu1(LH<T>::to_f(val) + bb));
+                    dst[row * RP + px] = val;
+                    if (++px == n) { px = 0; ++row; if (act && bias && row < D) bb = bias[row]; }
+                }
             }
         } else {
             for (int i = tid; i < (D << cwl); i += 256) {
@@ -216,16 +235,11 @@ __global__ void __launch_bounds__(256) recnext_linattn_mma_kernel(const T* __res
         }
         __syncthreads();
         // out = staged + pe, lanes along the pixels
-        int owl = 4;
-        while ((1 << owl) < cn) ++owl;
-        for (int i = tid; i < (D << owl); i += 256) {
-            const int j = i >> owl, px = i - (j << owl);
-            if (px >= cn) continue;
-            float val = LH<T>::to_f(b16[j * RP + px]);
-            const int pidx = c0 + px;
-            if (pep) val += LH<T>::to_f(pep[(long)j * n + pidx]);
-            if (pew) {   // + pe(v): depthwise 3x3 conv (+ bias) of v's plane j at this pixel
-                const int yy = pidx / pw, xx = pidx - yy * pw, ph = n / pw;
+        auto pe_of = [&](int j, int pidx, int yy, int xx) {   // pe[j, pixel]: a tensor, or the depthwise 3x3 conv (+ bias) of v's plane j at (yy, xx)
+            float add = 0.f;
+            if (pep) add = LH<T>::to_f(pep[(long)j * n + pidx]);
+            if (pew) {
+                const int ph = n / pw;
                 const float* wj = pew + (long)(h * D + j) * 9;
                 const unsigned short* vj = vp + (long)j * n;
                 float a9 = peb ? peb[h * D + j] : 0.f;
@@ -239,9 +253,35 @@ __global__ void __launch_bounds__(256) recnext_linattn_mma_kernel(const T* __res
                         if (x2 >= 0 && x2 < pw) a9 = fmaf(wj[(dy + 1) * 3 + dx + 1], LH<T>::to_f(vj[(long)y2 * pw + x2]), a9);
                     }
                 }
-                val += a9;
+                add += a9;
             }
-            op[(long)j * n + pidx] = LH<T>::from_f(val);
+            return add;
+        };
+        if (flat) {   // (single chunk) the [D x n] output block is contiguous: 16-byte stores of 8 flat elements
+            const int pwd = pew ? pw : n;
+            for (int i = tid; i < (D * n) / 8; i += 256) {
+                int j = (8 * i) / n, px = 8 * i - j * n;
+                int yy = px / pwd, xx = px - yy * pwd;
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float val = LH<T>::to_f(b16[j * RP + px]) + pe_of(j, px, yy, xx);
+                    w[e >> 1] |= (uint32_t)LH<T>::from_f(val) << (16 * (e & 1));
+                    if (++xx == pwd) { xx = 0; ++yy; }
+                    if (++px == n) { px = 0; ++j; yy = 0; xx = 0; }
+                }
+                reinterpret_cast<uint4*>(op)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            int owl = 4;
+            while ((1 << owl) < cn) ++owl;
+            for (int i = tid; i < (D << owl); i += 256) {
+                const int j = i >> owl, px = i - (j << owl);
+                if (px >= cn) continue;
+                const int pidx = c0 + px, pwd = pew ? pw : n;
+                const int yy = pidx / pwd, xx = pidx - yy * pwd;
+                op[(long)j * n + pidx] = LH<T>::from_f(LH<T>::to_f(b16[j * RP + px]) + pe_of(j, pidx, yy, xx));
+            }
         }
     }
 }
