@@ -22,7 +22,8 @@
 //               tile buffer (C >= 256) the tile is handed over in 64-channel slabs, each with its own barriers
 //   warps 12-15 output writers: staged rows + residual x -> out, lanes along the pixels (coalesced), row cursors, residual prefetched
 // Planes whose size is not a multiple of 4 pixels (7 x 7) are padded to a multiple of 8 columns in TILE space (FfnTcPlan::HWp): no 8-pixel
-// chunk straddles two images and the padding columns are never stored.
+// chunk straddles two images and the padding columns are never stored; loaders and writers of that path take one pixel per lane
+// (2-byte accesses, lanes along the pixels: coalesced) and walk down the channels.
 // All hand-offs are mbarriers; the MMA stream is software pipelined (GEMM1 of chunk s + 1 is issued before GEMM2 of chunk s) so the
 // tensor pipe works while the epilogue warps run the GELU of chunk s.
 #include <cuda_runtime.h>
@@ -94,6 +95,12 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void nb_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nb_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+__device__ __forceinline__ void sts16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ unsigned short lds16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -470,18 +477,35 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                     }
                     cp_async_arrive_noinc(bar(Y_FULL) + 8u * bi);
                 } else {
-                    const unsigned short* row = reinterpret_cast<const unsigned short*>(gy) + ca.o0;
-                    for (int kb = kbeg + k0; kb < kend; kb += 4 * KPP) {
-                        uint4 v[4];
+                    // Odd planes (7 x 7): no aligned vector covers an 8-pixel chunk, so the lanes run ALONG the tile's pixels (a warp's
+                    // 2-byte loads of one channel are consecutive addresses: 2-3 sectors per request, where a lane-per-chunk mapping
+                    // costs 32) and every lane walks down the channels of its pixel: pointer + HW in global, + 16 bytes in the tile.
+                    constexpr int NPOS = NT / (kLoadWarps * 32);
+                    constexpr int U = 64 / NPOS;                 // 64 two-byte loads in flight per lane
+                    const unsigned short* g16 = reinterpret_cast<const unsigned short*>(gy);
+                    const unsigned short* src[NPOS];
+                    uint32_t d[NPOS];
+                    bool ok[NPOS];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int k = kb + u * KPP;
-                            v[u] = (k < C) ? load8e(row + (long)k * HW, ca.nv) : make_uint4(0u, 0u, 0u, 0u);
-                        }
+                    for (int q = 0; q < NPOS; ++q) {
+                        const int m = lt + q * (kLoadWarps * 32);
+                        const Pix pm = pix_make((uint32_t)tile * NT + (uint32_t)m, (uint32_t)p.HWp);
+                        ok[q] = pm.b < ((p.dbg & 8) ? 0 : p.B) && pm.i < HW;
+                        src[q] = g16 + (ok[q] ? ((long)pm.b * C) * (long)HW + pm.i : 0) + (long)kbeg * HW;
+                        d[q] = sb + p.offY + ybuf * p.yBytes + (uint32_t)(m >> 3) * p.sboY + (uint32_t)(m & 7) * 2u + (uint32_t)kbeg * 16u;
+                    }
+                    for (int kb = kbeg; kb < kend; kb += U) {      // (kend - kbeg is a multiple of 16; U of 32 or 64 may overshoot: guarded)
+                        unsigned short e[NPOS][U];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int k = kb + u * KPP;
-                            if (k < kend) sts128(dst + (uint32_t)k * 16u, v[u].x, v[u].y, v[u].z, v[u].w);
+                        for (int q = 0; q < NPOS; ++q)
+#pragma unroll
+                            for (int u = 0; u < U; ++u) e[q][u] = (ok[q] && kb + u < C) ? __ldg(src[q] + (long)u * HW) : (unsigned short)0;
+#pragma unroll
+                        for (int q = 0; q < NPOS; ++q) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+                                if (kb + u < kend) sts16(d[q] + (uint32_t)u * 16u, e[q][u]);
+                            src[q] += (long)U * HW; d[q] += (uint32_t)U * 16u;
                         }
                     }
                     tc::mbar_arrive(bar(Y_FULL) + 8u * bi);
@@ -565,34 +589,49 @@ __global__ void __launch_bounds__(kThreads, 1) recnext_ffn_tc_kernel(const __gri
                     }
                 }
             } else {
-                const unsigned short* xrow = reinterpret_cast<const unsigned short*>(gx) + ca.o0;
-                unsigned short* orow = reinterpret_cast<unsigned short*>(gout) + cs.o0;
-                uint4 xr[PF];
+                // Odd planes: one tile pixel per lane (lanes along the pixels: coalesced 2-byte residual loads and stores), the lane
+                // walks down the staged channel rows; the residuals of a block of rows are in flight while the previous block is stored.
+                constexpr int NPL = (kWriteWarps * 32) / NT;     // row phases (NT = 64: two lanes per pixel, alternate rows)
+                constexpr int U = 16;
+                const int wl = (int)threadIdx.x - (kLoad0 + kLoadWarps * 32);
+                const int m = wl % NT, rph = wl / NT;
+                const Pix pm = pix_make((uint32_t)tile * NT + (uint32_t)m, (uint32_t)p.HWp);
+                const bool inimg = pm.b < p.B && pm.i < HW;
+                const bool okl = inimg && traffic && !(p.dbg & 16), oks = inimg && traffic && !(p.dbg & 32);
+                const long o = inimg ? ((long)pm.b * C) * (long)HW + pm.i : 0;
+                const unsigned short* xs = reinterpret_cast<const unsigned short*>(gx) + o;
+                unsigned short* os = reinterpret_cast<unsigned short*>(gout) + o;
+                const uint32_t st = sb + p.offH + grp * p.hBytes + (uint32_t)m * 2u;
+                for (int ct = 0; ct < nCT; ++ct) {
+                    const int c0 = ct * 128, rows = min(128, C - c0);
+                    unsigned short e[U];
 #pragma unroll
-                for (int u = 0; u < PF; ++u) { const int c = chan(u); xr[u] = c < C ? load8e(xrow + (long)c * HW, ca.nv) : make_uint4(0u, 0u, 0u, 0u); }
-                for (int jb = 0; jb < total; jb += PF) {
-                    if (jb % CH == 0) {
-                        tc::mbar_wait(bar(OUT_FULL) + 8u * grp, (grp ? ocnt1 : ocnt0) & 1u);
-                        nb_sync(3u + grp, 256u);
-                        if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH));
-                    }
+                    for (int u = 0; u < U; ++u) { const int r = rph + NPL * u; e[u] = (okl && r < rows) ? __ldg(xs + (long)(c0 + r) * HW) : (unsigned short)0; }
+                    tc::mbar_wait(bar(OUT_FULL) + 8u * grp, (grp ? ocnt1 : ocnt0) & 1u);
+                    nb_sync(3u + grp, 256u);
+                    if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * ct);
+                    for (int rb = 0; rb < rows; rb += U * NPL) {
+                        unsigned short cur[U];
 #pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        const int j = jb + u, it = j % CH, c = chan(j);
-                        uint32_t sw[4];
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage + (uint32_t)rowof(j) * SP));
-                        const uint4 xw = xr[u];
-                        if (j + PF < total) { const int cn = chan(j + PF); xr[u] = cn < C ? load8e(xrow + (long)cn * HW, ca.nv) : make_uint4(0u, 0u, 0u, 0u); }
-                        const uint4 w = make_uint4(Cvt<T>::add2(sw[0], xw.x), Cvt<T>::add2(sw[1], xw.y), Cvt<T>::add2(sw[2], xw.z), Cvt<T>::add2(sw[3], xw.w));
-                        if (c < C) store8e(orow + (long)c * HW, cs.nv, w);
+                        for (int u = 0; u < U; ++u) cur[u] = e[u];
+                        if (rb + U * NPL < rows) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) { const int r = rb + U * NPL + rph + NPL * u; e[u] = (okl && r < rows) ? __ldg(xs + (long)(c0 + r) * HW) : (unsigned short)0; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int r = rb + rph + NPL * u;
+                            if (r < rows) {
+                                const uint32_t w = Cvt<T>::add2((uint32_t)lds16(st + (uint32_t)r * SP), (uint32_t)cur[u]);
+                                if (oks) os[(long)(c0 + r) * HW] = (unsigned short)(w & 0xffffu);
+                            }
+                        }
                     }
-                    if ((jb + PF) % CH == 0 || jb + PF == total) {
-                        __syncwarp();
-                        nb_arrive(5u + grp, 256u);
-                        if (lane == 0) tc::mbar_arrive(bar(OUT_EMPTY) + 8u * grp);   // the staging buffer may be overwritten
-                        if (grp) ++ocnt1; else ++ocnt0;
-                        if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * (jb / CH) + 1);
-                    }
+                    __syncwarp();
+                    nb_arrive(5u + grp, 256u);
+                    if (lane == 0) tc::mbar_arrive(bar(OUT_EMPTY) + 8u * grp);   // the staging buffer may be overwritten
+                    if (grp) ++ocnt1; else ++ocnt0;
+                    if (warp == 10 + kLoadWarps) stamp(3, 256 + 4 * t + 2 * ct + 1);
                 }
             }
         }
