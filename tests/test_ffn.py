@@ -60,7 +60,8 @@ def test_ffn_forward_has_no_cpu_path():
 # C % 16 != 0 (zero-padded K), hidden % 128 != 0, more tiles than SMs
 _FFN_CASES = [(4, 64, 56, 56, 128), (4, 128, 28, 28, 256), (3, 256, 14, 14, 512), (3, 512, 7, 7, 1024), (3, 80, 28, 28, 160), (2, 160, 14, 14, 320),
               (5, 320, 14, 14, 640), (3, 640, 7, 7, 1280), (2, 40, 56, 56, 80), (2, 64, 56, 56, 120), (2, 128, 28, 28, 240), (2, 32, 6, 6, 64),
-              (2, 48, 10, 18, 96), (3, 24, 5, 7, 40), (64, 64, 56, 56, 128), (2, 256, 50, 84, 512)]
+              (2, 48, 10, 18, 96), (3, 24, 5, 7, 40), (64, 64, 56, 56, 128), (2, 256, 50, 84, 512),
+              (7, 64, 7, 7, 128), (2, 152, 9, 13, 304), (37, 320, 7, 7, 600)]   # odd planes: pixel-per-lane loaders / writers, partial channel tiles
 
 
 @pytest.mark.gpu
